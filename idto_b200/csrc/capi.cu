@@ -1,0 +1,751 @@
+// C ABI of the idto_b200 CUDA layer (include/idto_b200.h) and the host-side driver that enqueues
+// the kernel family.  There is NO CPU fallback: without a CUDA device every entry point that needs
+// one returns IDTO_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "dynamics.cuh"
+#include "solver.h"
+
+namespace idto {
+
+long g_launch_counter = 0;
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+struct DevAlloc {
+  std::vector<void*> ptrs;
+  template <typename T>
+  cudaError_t get(T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(q, 0, std::max<size_t>(count, 1) * sizeof(T));
+    ptrs.push_back(q);
+    *p = static_cast<T*>(q);
+    return e;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+}  // namespace idto
+
+using namespace idto;
+
+struct idto_model_s {
+  DevModel dm;
+  DevAlloc mem;
+  int device;
+  std::vector<int> unactuated, quat_starts;
+  std::vector<int> jtype, qs, vs;
+  int nq, nv;
+};
+
+struct ProfEvent {
+  cudaEvent_t a, b;
+};
+
+struct idto_solver_s {
+  idto_model_t model;
+  SolverConsts sc;
+  SolverBufs bf;
+  DevAlloc mem;
+  cudaStream_t stream = nullptr;
+  int device;
+  idto_params params;
+  // mutable per-batch problem data
+  double *q_init, *v_init, *q_nom, *v_nom;
+  long launches0 = 0;
+  bool profile = false;
+  std::map<std::string, std::vector<ProfEvent>> prof;
+  std::vector<ProbCtl> ctl_host;
+  size_t stats_cap = 0;
+};
+
+namespace {
+
+int check_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    set_last_error("no CUDA device available; idto_b200 has no CPU fallback");
+    return IDTO_ERR_NO_DEVICE;
+  }
+  return IDTO_OK;
+}
+
+bool is_diag(const double* Mx, int n) {
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i)
+      if (i != j && Mx[size_t(j) * n + i] != 0.0) return false;
+  return true;
+}
+
+struct Prof {
+  idto_solver_s* s;
+  const char* name;
+  ProfEvent ev{};
+  Prof(idto_solver_s* s_, const char* n) : s(s_), name(n) {
+    if (s->profile) {
+      cudaEventCreate(&ev.a), cudaEventCreate(&ev.b);
+      cudaEventRecord(ev.a, s->stream);
+    }
+  }
+  ~Prof() {
+    if (s->profile) {
+      cudaEventRecord(ev.b, s->stream);
+      s->prof[name].push_back(ev);
+    }
+  }
+};
+
+// Stage pipeline; each stage is gated on the per-problem dirty flags unless force is set.
+void enqueue_trajectory(idto_solver_s* s, bool scratch, bool force) {
+  Prof p(s, scratch ? "trajectory_scratch" : "trajectory");
+  launch_traj(s->model->dm, s->sc, s->bf, scratch, force, s->stream);
+  launch_tau(s->model->dm, s->sc, s->bf, scratch, force, s->stream);
+}
+void enqueue_derivatives(idto_solver_s* s, bool force) {
+  Prof p(s, "id_partials");
+  launch_partials(s->model->dm, s->sc, s->bf, force, s->stream);
+}
+void enqueue_assembly(idto_solver_s* s, bool force) {
+  {
+    Prof p(s, "assemble");
+    launch_assemble(s->model->dm, s->sc, s->bf, force, s->stream);
+  }
+  {
+    Prof p(s, "factor");
+    launch_factor(s->sc, s->bf, force, s->stream);
+  }
+  {
+    Prof p(s, "lagrange");
+    launch_lagrange(s->model->dm, s->sc, s->bf, force, s->stream);
+  }
+}
+void enqueue_iteration(idto_solver_s* s) {
+  enqueue_trajectory(s, false, false);
+  enqueue_derivatives(s, false);
+  enqueue_assembly(s, false);
+  if (s->sc.check_convergence) launch_conv_check(s->sc, s->bf, s->stream);
+  {
+    Prof p(s, "dogleg");
+    launch_dogleg(s->sc, s->bf, s->stream);
+  }
+  enqueue_trajectory(s, true, true);
+  {
+    Prof p(s, "trust_update");
+    launch_trust_update(s->model->dm, s->sc, s->bf, true, s->stream);
+  }
+}
+
+__global__ void k_set_ctl(ProbCtl* ctl, int B, int what, double Delta0) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (what == 0) {  // creation
+    ctl[b].Delta = Delta0, ctl[b].traj_dirty = 1, ctl[b].derivs_dirty = 1, ctl[b].active = 1;
+    ctl[b].iters = 0, ctl[b].reason = 0, ctl[b].pending = 0, ctl[b].tr_active = 0;
+  } else if (what == 1) {  // q / problem changed: invalidate all caches (state.h:333-350)
+    ctl[b].traj_dirty = 1, ctl[b].derivs_dirty = 1, ctl[b].pending = 0;
+  } else if (what == 2) {  // solve start
+    ctl[b].active = 1, ctl[b].iters = 0, ctl[b].reason = 0, ctl[b].pending = 0;
+  }
+}
+__global__ void k_set_prev_cost(ProbCtl* ctl, const double* cost, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) ctl[b].prev_cost = cost[b];
+}
+__global__ void k_set_delta(ProbCtl* ctl, const double* d, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) ctl[b].Delta = d[b];
+}
+__global__ void k_fill(double* p, size_t n, double v) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = v;
+}
+// Constant part of N+ (identity pattern for 1-dof / planar joints and floating translations).
+__global__ void k_init_nplus(DevModel dm, double* Np, int B, int T) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * (T + 1)) return;
+  double* N = Np + size_t(idx) * dm.nv * dm.nq;
+  const int* jtype = dm.itab + dm.o_jtype;
+  const int* qs = dm.itab + dm.o_qs;
+  const int* vs = dm.itab + dm.o_vs;
+  for (int k = 0; k < dm.nb; ++k) {
+    if (jtype[k] == IDTO_JOINT_QUAT_FLOATING) {
+      for (int i = 0; i < 3; ++i) N[size_t(qs[k] + 4 + i) * dm.nv + vs[k] + 3 + i] = 1.0;
+    } else {
+      const int n = jtype[k] == IDTO_JOINT_PLANAR ? 3 : 1;
+      for (int i = 0; i < n; ++i) N[size_t(qs[k] + i) * dm.nv + vs[k] + i] = 1.0;
+    }
+  }
+}
+
+int ensure_stats(idto_solver_s* s, size_t cap) {
+  if (cap <= s->stats_cap) return IDTO_OK;
+  double* p = nullptr;
+  IDTO_CUDA_CHECK(cudaMalloc(&p, cap * s->sc.B * IDTO_NUM_STATS * sizeof(double)));
+  s->mem.ptrs.push_back(p);
+  s->bf.stats = p;
+  s->bf.stats_cap = int(cap);
+  s->stats_cap = cap;
+  return IDTO_OK;
+}
+
+int check_status(idto_solver_s* s) {
+  int st = 0;
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(&st, s->bf.status, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  IDTO_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+  if (st != 0) {
+    set_last_error("penta-diagonal factorisation failed (singular diagonal block)");
+    int zero = 0;
+    cudaMemcpyAsync(s->bf.status, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream);
+    return st;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error(std::string("kernel launch: ") + cudaGetErrorString(e));
+    return IDTO_ERR_CUDA;
+  }
+  return IDTO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* idto_last_error(void) { return g_last_error.c_str(); }
+
+int idto_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void idto_params_default(idto_params* p) {  // optimizer/solver_parameters.h:64-167
+  std::memset(p, 0, sizeof(*p));
+  p->max_iterations = 100, p->gradients_method = IDTO_GRAD_FORWARD, p->normalize_quaternions = 0;
+  p->contact_stiffness = 100, p->dissipation_velocity = 0.1, p->stiction_velocity = 0.05;
+  p->friction_coefficient = 0.5, p->smoothing_factor = 0.1, p->scaling = 1;
+  p->scaling_method = IDTO_SCALING_DOUBLE_SQRT, p->equality_constraints = 1;
+  p->Delta0 = 1e-1, p->Delta_max = 1e5, p->check_convergence = 0, p->linear_solver = IDTO_LINSOLVE_THOMAS;
+}
+
+int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
+  if (!d || !out) return IDTO_ERR_INVALID_ARG;
+  if (int rc = check_device()) return rc;
+  if (d->nbodies < 1 || d->nbodies > kMaxGroup) {
+    set_last_error("model has " + std::to_string(d->nbodies) + " moving bodies; supported: 1.." +
+                   std::to_string(kMaxGroup));
+    return IDTO_ERR_UNSUPPORTED;
+  }
+  const int nb = d->nbodies, ng = d->ngeoms, np = d->npairs;
+  for (int i = 0; i < ng; ++i)
+    if (d->geom_type[i] != IDTO_GEOM_SPHERE && d->geom_type[i] != IDTO_GEOM_BOX) return IDTO_ERR_UNSUPPORTED;
+  for (int i = 0; i < np; ++i)
+    if (d->geom_type[d->pair_geomA[i]] == IDTO_GEOM_BOX && d->geom_type[d->pair_geomB[i]] == IDTO_GEOM_BOX) {
+      set_last_error("box-box contact pairs have no closed-form signed distance here");
+      return IDTO_ERR_UNSUPPORTED;
+    }
+  auto* m = new idto_model_s();
+  cudaGetDevice(&m->device);
+  int G = 2;
+  while (G < nb) G *= 2;
+  const int nbp = G, npp = std::max(2, (np + 1) / 2 * 2), ngp = std::max(ng, 1);
+  // levels / children
+  std::vector<int> level(nb), nchild(nb, 0), child(size_t(kMaxChildren) * nbp, 0);
+  int nlevels = 0;
+  for (int k = 0; k < nb; ++k) {
+    const int p = d->parent[k];
+    if (p >= k) {
+      delete m;
+      set_last_error("bodies must be topologically ordered");
+      return IDTO_ERR_INVALID_ARG;
+    }
+    level[k] = p < 0 ? 0 : level[p] + 1;
+    nlevels = std::max(nlevels, level[k] + 1);
+    if (p >= 0) {
+      if (nchild[p] >= kMaxChildren) {
+        delete m;
+        set_last_error("more than kMaxChildren children on one body");
+        return IDTO_ERR_UNSUPPORTED;
+      }
+      child[size_t(nchild[p]) * nbp + p] = k;
+      nchild[p]++;
+    }
+  }
+  // int table
+  std::vector<int> it;
+  auto push_i = [&](const int* src, int n, int padded) {
+    const int off = int(it.size());
+    for (int i = 0; i < padded; ++i) it.push_back(i < n ? src[i] : 0);
+    return off;
+  };
+  DevModel& dm = m->dm;
+  dm.nb = nb, dm.nbp = nbp, dm.nq = d->nq, dm.nv = d->nv, dm.ng = ngp, dm.np = np, dm.npp = npp;
+  dm.nlevels = nlevels, dm.group = G;
+  dm.gx = d->gravity[0], dm.gy = d->gravity[1], dm.gz = d->gravity[2];
+  std::vector<int> parent_p(nbp, -1);
+  for (int k = 0; k < nb; ++k) parent_p[k] = d->parent[k];
+  dm.o_parent = push_i(parent_p.data(), nbp, nbp);
+  dm.o_jtype = push_i(d->joint_type, nb, nbp);
+  dm.o_qs = push_i(d->q_start, nb, nbp);
+  dm.o_vs = push_i(d->v_start, nb, nbp);
+  dm.o_level = push_i(level.data(), nb, nbp);
+  dm.o_nchild = push_i(nchild.data(), nb, nbp);
+  dm.o_child = push_i(child.data(), kMaxChildren * nbp, kMaxChildren * nbp);
+  std::vector<int> flags(nbp, 0), qowner(d->nq, 0);
+  for (int k = 0; k < nb; ++k) {
+    const double* R = d->R_MB + 9 * k;
+    bool ident = true;
+    for (int e = 0; e < 9; ++e) ident &= (R[e] == ((e % 4 == 0) ? 1.0 : 0.0));
+    flags[k] = ident ? 1 : 0;
+    const int jt = d->joint_type[k];
+    const int nqb = jt == IDTO_JOINT_QUAT_FLOATING ? 7 : (jt == IDTO_JOINT_PLANAR ? 3 : 1);
+    for (int i = 0; i < nqb; ++i) qowner[d->q_start[k] + i] = k;
+    if (jt == IDTO_JOINT_QUAT_FLOATING) m->quat_starts.push_back(d->q_start[k]);
+  }
+  dm.o_flags = push_i(flags.data(), nbp, nbp);
+  dm.o_qowner = push_i(qowner.data(), d->nq, d->nq);
+  dm.o_gbody = push_i(d->geom_body, ng, ngp);
+  dm.o_gtype = push_i(d->geom_type, ng, ngp);
+  dm.o_pA = push_i(d->pair_geomA, np, npp);
+  dm.o_pB = push_i(d->pair_geomB, np, npp);
+  while (it.size() % 4) it.push_back(0);
+  // double table (SoA: field-major, body-minor)
+  std::vector<double> dt;
+  auto push_soa = [&](const double* src, int fields, int n, int stride) {
+    const int off = int(dt.size());
+    for (int f = 0; f < fields; ++f)
+      for (int i = 0; i < stride; ++i) dt.push_back(i < n ? src[size_t(i) * fields + f] : 0.0);
+    return off;
+  };
+  dm.o_XPF = push_soa(d->X_PF, 12, nb, nbp);
+  dm.o_RMB = push_soa(d->R_MB, 9, nb, nbp);
+  dm.o_axis = push_soa(d->axis, 3, nb, nbp);
+  dm.o_mass = push_soa(d->mass, 1, nb, nbp);
+  dm.o_com = push_soa(d->com, 3, nb, nbp);
+  dm.o_inertia = push_soa(d->inertia, 6, nb, nbp);
+  dm.o_damping = push_soa(d->damping, 1, d->nv, d->nv);
+  dm.o_gdims = push_soa(d->geom_dims, 3, ng, ngp);
+  dm.o_XBG = push_soa(d->X_BG, 12, ng, ngp);
+  while (dt.size() % 2) dt.push_back(0.0);
+  dm.itab_bytes = int(it.size() * sizeof(int));
+  dm.dtab_bytes = int(dt.size() * sizeof(double));
+  int* di = nullptr;
+  double* dd = nullptr;
+  if (m->mem.get(&di, it.size()) != cudaSuccess || m->mem.get(&dd, dt.size()) != cudaSuccess ||
+      cudaMemcpy(di, it.data(), dm.itab_bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(dd, dt.data(), dm.dtab_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_last_error("cudaMalloc/cudaMemcpy failed for the model tables");
+    m->mem.release();
+    delete m;
+    return IDTO_ERR_CUDA;
+  }
+  dm.itab = di, dm.dtab = dd;
+  // cc:63-72: unactuated dofs (fully actuated if the actuation matrix is empty)
+  bool any = false;
+  for (int i = 0; i < d->nv; ++i) any |= d->actuated[i] != 0;
+  if (any)
+    for (int i = 0; i < d->nv; ++i)
+      if (!d->actuated[i]) m->unactuated.push_back(i);
+  m->nq = d->nq, m->nv = d->nv;
+  m->jtype.assign(d->joint_type, d->joint_type + nb);
+  m->qs.assign(d->q_start, d->q_start + nb);
+  m->vs.assign(d->v_start, d->v_start + nb);
+  *out = m;
+  return IDTO_OK;
+}
+
+int idto_model_destroy(idto_model_t m) {
+  if (!m) return IDTO_ERR_INVALID_ARG;
+  m->mem.release();
+  delete m;
+  return IDTO_OK;
+}
+int idto_model_num_unactuated(idto_model_t m) { return m ? int(m->unactuated.size()) : IDTO_ERR_INVALID_ARG; }
+int idto_model_unactuated_dofs(idto_model_t m, int* out) {
+  if (!m || !out) return IDTO_ERR_INVALID_ARG;
+  std::copy(m->unactuated.begin(), m->unactuated.end(), out);
+  return IDTO_OK;
+}
+
+int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_params* p, int batch,
+                       idto_solver_t* out) {
+  if (!m || !pd || !p || !out || batch < 1 || pd->num_steps < 1 || !(pd->time_step > 0)) return IDTO_ERR_INVALID_ARG;
+  if (int rc = check_device()) return rc;
+  const int nq = m->nq, nv = m->nv, T = pd->num_steps, B = batch;
+  if (!is_diag(pd->Qq, nq) || !is_diag(pd->Qv, nv) || !is_diag(pd->Qf_q, nq) || !is_diag(pd->Qf_v, nv) ||
+      !is_diag(pd->R, nv)) {
+    set_last_error("only diagonal cost weights are supported by the CUDA path");
+    return IDTO_ERR_UNSUPPORTED;
+  }
+  if (p->gradients_method < IDTO_GRAD_FORWARD || p->gradients_method > IDTO_GRAD_CENTRAL4) {
+    set_last_error("gradients_method must be forward, central or central4 (autodiff needs Drake scalars)");
+    return IDTO_ERR_UNSUPPORTED;
+  }
+  auto* s = new idto_solver_s();
+  s->model = m, s->params = *p;
+  cudaGetDevice(&s->device);
+  SolverConsts& sc = s->sc;
+  sc.B = B, sc.T = T, sc.nq = nq, sc.nv = nv, sc.nu = int(m->unactuated.size());
+  sc.n = (T + 1) * nq, sc.nh = sc.nu * T, sc.dt = pd->time_step;
+  sc.method = p->gradients_method, sc.scaling = p->scaling, sc.scaling_method = p->scaling_method;
+  sc.eq = p->equality_constraints && sc.nh > 0, sc.normalize_quat = p->normalize_quaternions;
+  sc.check_convergence = p->check_convergence;
+  sc.k = p->contact_stiffness, sc.sigma = p->smoothing_factor, sc.vd = p->dissipation_velocity;
+  sc.vs = p->stiction_velocity, sc.mu = p->friction_coefficient;
+  const double eps = std::sqrt(std::numeric_limits<double>::epsilon());
+  sc.threshold = -sc.sigma * std::log(std::exp(eps / (sc.sigma * sc.k)) - 1.0);  // cc:268-269
+  sc.Delta_max = p->Delta_max;
+  sc.tol[0] = p->tol_rel_cost_reduction, sc.tol[1] = p->tol_abs_cost_reduction;
+  sc.tol[2] = p->tol_rel_gradient_along_dq, sc.tol[3] = p->tol_abs_gradient_along_dq;
+  sc.tol[4] = p->tol_rel_state_change, sc.tol[5] = p->tol_abs_state_change;
+  sc.nquat = int(m->quat_starts.size());
+
+  DevAlloc& A = s->mem;
+  SolverBufs& bf = s->bf;
+  bool ok = true;
+  auto alloc = [&](double** ptr, size_t n) { ok = ok && (A.get(ptr, n) == cudaSuccess); };
+  double *dQq, *dQv, *dQfq, *dQfv, *dR;
+  alloc(&dQq, nq), alloc(&dQv, nv), alloc(&dQfq, nq), alloc(&dQfv, nv), alloc(&dR, nv);
+  int *dun = nullptr, *dqs = nullptr;
+  ok = ok && A.get(&dun, m->unactuated.size()) == cudaSuccess && A.get(&dqs, m->quat_starts.size()) == cudaSuccess;
+  const size_t nTq = size_t(B) * (T + 1) * nq, nTv = size_t(B) * (T + 1) * nv, nA = size_t(B) * T * nv;
+  const size_t nN = size_t(B) * (T + 1) * nv * nq, nP = size_t(B) * T * nv * nq, nH = size_t(B) * (T + 1) * nq * nq;
+  const size_t nh = std::max(sc.nh, 1), nvar = size_t(B) * sc.n;
+  for (TrajBuf* tb : {&bf.st, &bf.sc}) {
+    alloc(&tb->q, nTq), alloc(&tb->v, nTv), alloc(&tb->a, nA), alloc(&tb->tau, nA), alloc(&tb->Nplus, nN);
+    alloc(&tb->cost, B), alloc(&tb->h, size_t(B) * nh);
+  }
+  alloc(&s->q_init, size_t(B) * nq), alloc(&s->v_init, size_t(B) * nv), alloc(&s->q_nom, nTq), alloc(&s->v_nom, nTv);
+  alloc(&bf.dqm, nP), alloc(&bf.dqt, nP), alloc(&bf.dqp, nP);
+  alloc(&bf.g, nvar), alloc(&bf.D, nvar), alloc(&bf.gs, nvar), alloc(&bf.gm, nvar);
+  alloc(&bf.lambda, size_t(B) * nh), alloc(&bf.merit, B);
+  alloc(&bf.HA, nH), alloc(&bf.HB, nH), alloc(&bf.HC, nH), alloc(&bf.SA, nH), alloc(&bf.SB, nH), alloc(&bf.SC, nH);
+  const size_t nJ = size_t(B) * T * std::max(sc.nu, 1) * nq;
+  alloc(&bf.Jm, nJ), alloc(&bf.Jt, nJ), alloc(&bf.Jp, nJ);
+  alloc(&bf.FK, nH), alloc(&bf.FG, nH), alloc(&bf.FY, nH), alloc(&bf.FZ, nH);
+  alloc(&bf.X, sc.eq ? size_t(B) * nh * sc.n : 1), alloc(&bf.S, sc.eq ? size_t(B) * nh * nh : 1);
+  alloc(&bf.rhs, size_t(B) * nh);
+  alloc(&bf.pH, nvar), alloc(&bf.dq, nvar), alloc(&bf.dqH, nvar), alloc(&bf.tmp1, nvar), alloc(&bf.tmp2, nvar);
+  alloc(&bf.red, size_t(B) * 8);
+  ok = ok && A.get(&bf.ctl, B) == cudaSuccess && A.get(&bf.status, 1) == cudaSuccess;
+  if (!ok) {
+    set_last_error("cudaMalloc failed while creating the solver workspace");
+    A.release();
+    delete s;
+    return IDTO_ERR_CUDA;
+  }
+  bf.q_init = s->q_init, bf.v_init = s->v_init, bf.q_nom = s->q_nom, bf.v_nom = s->v_nom;
+  bf.stats = nullptr, bf.stats_cap = 0;
+  sc.Qq = dQq, sc.Qv = dQv, sc.Qfq = dQfq, sc.Qfv = dQfv, sc.R = dR, sc.unact = dun, sc.quat_starts = dqs;
+  auto up_diag = [&](double* dst, const double* Mx, int n) {
+    std::vector<double> dg(n);
+    for (int i = 0; i < n; ++i) dg[i] = Mx[size_t(i) * n + i];
+    cudaMemcpy(dst, dg.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  up_diag(dQq, pd->Qq, nq), up_diag(dQv, pd->Qv, nv), up_diag(dQfq, pd->Qf_q, nq), up_diag(dQfv, pd->Qf_v, nv);
+  up_diag(dR, pd->R, nv);
+  cudaMemcpy(dun, m->unactuated.data(), m->unactuated.size() * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(dqs, m->quat_starts.data(), m->quat_starts.size() * sizeof(int), cudaMemcpyHostToDevice);
+  // broadcast the template problem to every batch element
+  for (int b = 0; b < B; ++b) {
+    cudaMemcpy(s->q_init + size_t(b) * nq, pd->q_init, nq * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(s->v_init + size_t(b) * nv, pd->v_init, nv * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(s->q_nom + size_t(b) * (T + 1) * nq, pd->q_nom, size_t(T + 1) * nq * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(s->v_nom + size_t(b) * (T + 1) * nv, pd->v_nom, size_t(T + 1) * nv * sizeof(double), cudaMemcpyHostToDevice);
+  }
+  // preset entries (inverse_dynamics_partials.h:35-42; state.h:68)
+  const size_t blk = size_t(nv) * nq;
+  for (int b = 0; b < B; ++b) k_fill<<<1, 128>>>(bf.dqm + size_t(b) * T * blk, blk, std::numeric_limits<double>::quiet_NaN());
+  k_fill<<<64, 256>>>(bf.D, nvar, 1.0);
+  k_init_nplus<<<(B * (T + 1) + 127) / 128, 128>>>(m->dm, bf.st.Nplus, B, T);
+  k_init_nplus<<<(B * (T + 1) + 127) / 128, 128>>>(m->dm, bf.sc.Nplus, B, T);
+  k_set_ctl<<<(B + 127) / 128, 128>>>(bf.ctl, B, 0, p->Delta0);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_last_error("solver initialisation kernels failed");
+    A.release();
+    delete s;
+    return IDTO_ERR_CUDA;
+  }
+  s->ctl_host.resize(B);
+  s->launches0 = g_launch_counter;
+  *out = s;
+  return IDTO_OK;
+}
+
+int idto_solver_destroy(idto_solver_t s) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaDeviceSynchronize();
+  for (auto& kv : s->prof)
+    for (auto& e : kv.second) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
+  s->mem.release();
+  delete s;
+  return IDTO_OK;
+}
+
+int idto_solver_set_stream(idto_solver_t s, void* stream) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  s->stream = static_cast<cudaStream_t>(stream);
+  return IDTO_OK;
+}
+
+int idto_set_q(idto_solver_t s, const double* q) {
+  if (!s || !q) return IDTO_ERR_INVALID_ARG;
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(s->bf.st.q, q, size_t(s->sc.B) * s->sc.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 1, 0.0);
+  return IDTO_OK;
+}
+int idto_reset_initial_conditions(idto_solver_t s, const double* q0, const double* v0) {
+  if (!s || !q0 || !v0) return IDTO_ERR_INVALID_ARG;
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(s->q_init, q0, size_t(s->sc.B) * s->sc.nq * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(s->v_init, v0, size_t(s->sc.B) * s->sc.nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 1, 0.0);
+  return IDTO_OK;
+}
+int idto_update_nominal_trajectory(idto_solver_t s, const double* qn, const double* vn) {
+  if (!s || !qn || !vn) return IDTO_ERR_INVALID_ARG;
+  const size_t T1 = s->sc.T + 1;
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(s->q_nom, qn, size_t(s->sc.B) * T1 * s->sc.nq * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(s->v_nom, vn, size_t(s->sc.B) * T1 * s->sc.nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 1, 0.0);
+  return IDTO_OK;
+}
+int idto_set_delta(idto_solver_t s, const double* delta) {
+  if (!s || !delta) return IDTO_ERR_INVALID_ARG;
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(s->bf.red, delta, s->sc.B * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  k_set_delta<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->bf.red, s->sc.B);
+  return IDTO_OK;
+}
+int idto_get_delta(idto_solver_t s, double* delta) { return idto_get(s, "delta", delta); }
+
+int idto_eval_trajectory(idto_solver_t s) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  enqueue_trajectory(s, false, false);
+  return check_status(s);
+}
+int idto_eval_derivatives(idto_solver_t s) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  enqueue_trajectory(s, false, false);
+  enqueue_derivatives(s, false);
+  return check_status(s);
+}
+int idto_eval_assembly(idto_solver_t s) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  enqueue_trajectory(s, false, false);
+  enqueue_derivatives(s, false);
+  enqueue_assembly(s, false);
+  launch_clear_dirty(s->sc, s->bf, s->stream);
+  return check_status(s);
+}
+int idto_eval_dogleg(idto_solver_t s) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  if (int rc = idto_eval_assembly(s)) return rc;
+  k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 2, 0.0);
+  launch_dogleg(s->sc, s->bf, s->stream);
+  return check_status(s);
+}
+int idto_eval_trust_ratio(idto_solver_t s) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  if (int rc = idto_eval_dogleg(s)) return rc;
+  enqueue_trajectory(s, true, true);
+  launch_trust_update(s->model->dm, s->sc, s->bf, false, s->stream);
+  return check_status(s);
+}
+
+long idto_field_size(idto_solver_t s, const char* field) {
+  if (!s || !field) return IDTO_ERR_INVALID_ARG;
+  const SolverConsts& c = s->sc;
+  const std::string f(field);
+  const long T = c.T, nq = c.nq, nv = c.nv;
+  if (f == "q") return (T + 1) * nq;
+  if (f == "v") return (T + 1) * nv;
+  if (f == "a" || f == "tau") return T * nv;
+  if (f == "Nplus") return (T + 1) * nv * nq;
+  if (f == "cost" || f == "merit" || f == "dq_active" || f == "rho" || f == "delta") return 1;
+  if (f == "h" || f == "lambda") return c.nh;
+  if (f == "dtau_dqm" || f == "dtau_dqt" || f == "dtau_dqp") return T * nv * nq;
+  if (f == "g" || f == "D" || f == "gs" || f == "gm" || f == "dq" || f == "dqH") return c.n;
+  if (f == "H_A" || f == "H_B" || f == "H_C" || f == "Hs_A" || f == "Hs_B" || f == "Hs_C") return (T + 1) * nq * nq;
+  if (f == "J") return long(c.nh) * c.n;
+  return IDTO_ERR_INVALID_ARG;
+}
+
+int idto_get(idto_solver_t s, const char* field, double* out) {
+  if (!s || !field || !out) return IDTO_ERR_INVALID_ARG;
+  const long sz = idto_field_size(s, field);
+  if (sz < 0) return IDTO_ERR_INVALID_ARG;
+  const SolverConsts& c = s->sc;
+  const SolverBufs& bf = s->bf;
+  const std::string f(field);
+  IDTO_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+  const double* src = nullptr;
+  if (f == "q") src = bf.st.q;
+  else if (f == "v") src = bf.st.v;
+  else if (f == "a") src = bf.st.a;
+  else if (f == "tau") src = bf.st.tau;
+  else if (f == "Nplus") src = bf.st.Nplus;
+  else if (f == "cost") src = bf.st.cost;
+  else if (f == "h") src = bf.st.h;
+  else if (f == "dtau_dqm") src = bf.dqm;
+  else if (f == "dtau_dqt") src = bf.dqt;
+  else if (f == "dtau_dqp") src = bf.dqp;
+  else if (f == "g") src = bf.g;
+  else if (f == "H_A") src = bf.HA;
+  else if (f == "H_B") src = bf.HB;
+  else if (f == "H_C") src = bf.HC;
+  else if (f == "D") src = bf.D;
+  else if (f == "Hs_A") src = bf.SA;
+  else if (f == "Hs_B") src = bf.SB;
+  else if (f == "Hs_C") src = bf.SC;
+  else if (f == "gs") src = bf.gs;
+  else if (f == "lambda") src = bf.lambda;
+  else if (f == "merit") src = bf.merit;
+  else if (f == "gm") src = bf.gm;
+  else if (f == "dq") src = bf.dq;
+  else if (f == "dqH") src = bf.dqH;
+  if (src) {
+    IDTO_CUDA_CHECK(cudaMemcpy(out, src, size_t(sz) * c.B * sizeof(double), cudaMemcpyDeviceToHost));
+    return IDTO_OK;
+  }
+  if (f == "J") {  // expand the three bands into the reference's dense (nu*T) x n, column-major
+    const size_t nJ = size_t(c.B) * c.T * std::max(c.nu, 1) * c.nq;
+    std::vector<double> jm(nJ), jt(nJ), jp(nJ);
+    IDTO_CUDA_CHECK(cudaMemcpy(jm.data(), bf.Jm, nJ * sizeof(double), cudaMemcpyDeviceToHost));
+    IDTO_CUDA_CHECK(cudaMemcpy(jt.data(), bf.Jt, nJ * sizeof(double), cudaMemcpyDeviceToHost));
+    IDTO_CUDA_CHECK(cudaMemcpy(jp.data(), bf.Jp, nJ * sizeof(double), cudaMemcpyDeviceToHost));
+    std::fill(out, out + size_t(sz) * c.B, 0.0);
+    for (int b = 0; b < c.B; ++b)
+      for (int t = 0; t < c.T; ++t)
+        for (int u = 0; u < c.nu; ++u) {
+          const size_t jb = ((size_t(b) * c.T + t) * c.nu + u) * c.nq;
+          const size_t row = size_t(t) * c.nu + u;
+          double* J = out + size_t(b) * sz;
+          for (int cc = 0; cc < c.nq; ++cc) {
+            J[(size_t(t + 1) * c.nq + cc) * c.nh + row] = jp[jb + cc];
+            if (t > 0) J[(size_t(t) * c.nq + cc) * c.nh + row] = jt[jb + cc];
+            if (t > 1) J[(size_t(t - 1) * c.nq + cc) * c.nh + row] = jm[jb + cc];
+          }
+        }
+    return IDTO_OK;
+  }
+  IDTO_CUDA_CHECK(cudaMemcpy(s->ctl_host.data(), bf.ctl, c.B * sizeof(ProbCtl), cudaMemcpyDeviceToHost));
+  for (int b = 0; b < c.B; ++b) {
+    const ProbCtl& k = s->ctl_host[b];
+    out[b] = f == "rho" ? k.rho : (f == "delta" ? k.Delta : double(k.tr_active));
+  }
+  return IDTO_OK;
+}
+
+static int solve_enqueue(idto_solver_t s, int max_iterations) {
+  if (int rc = ensure_stats(s, size_t(max_iterations))) return rc;
+  k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 2, 0.0);
+  if (s->sc.check_convergence) {
+    // previous_cost = EvalCost(state) (cc:2494)
+    enqueue_trajectory(s, false, false);
+    k_set_prev_cost<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->bf.st.cost, s->sc.B);
+  }
+  for (int k = 0; k < max_iterations; ++k) enqueue_iteration(s);
+  if (s->sc.check_convergence) {
+    // the check of the last accepted step needs the new state's merit gradient (cc:2604, 2673)
+    enqueue_trajectory(s, false, false);
+    enqueue_derivatives(s, false);
+    enqueue_assembly(s, false);
+    launch_conv_check(s->sc, s->bf, s->stream);
+    launch_clear_dirty(s->sc, s->bf, s->stream);
+  }
+  return IDTO_OK;
+}
+
+static int solve_collect(idto_solver_t s, int max_iterations, int* iters_out, int* reason_out, double* stats_out) {
+  const int B = s->sc.B;
+  IDTO_CUDA_CHECK(cudaMemcpy(s->ctl_host.data(), s->bf.ctl, B * sizeof(ProbCtl), cudaMemcpyDeviceToHost));
+  for (int b = 0; b < B; ++b) {
+    if (iters_out) iters_out[b] = s->ctl_host[b].iters;
+    if (reason_out) reason_out[b] = s->ctl_host[b].reason;
+  }
+  if (stats_out) {
+    for (int b = 0; b < B; ++b)
+      IDTO_CUDA_CHECK(cudaMemcpy(stats_out + size_t(b) * max_iterations * IDTO_NUM_STATS,
+                                 s->bf.stats + size_t(b) * s->bf.stats_cap * IDTO_NUM_STATS,
+                                 size_t(max_iterations) * IDTO_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return IDTO_OK;
+}
+
+int idto_solve(idto_solver_t s, int max_iterations, int* iters_out, int* reason_out, double* stats_out) {
+  if (!s || max_iterations < 0) return IDTO_ERR_INVALID_ARG;
+  if (int rc = solve_enqueue(s, max_iterations)) return rc;
+  if (int rc = check_status(s)) return rc;
+  return solve_collect(s, max_iterations, iters_out, reason_out, stats_out);
+}
+
+int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_guess, const double* q_init,
+                       const double* v_init, const double* q_nom, const double* v_nom, double* q_out, double* v_out,
+                       double* tau_out, int* iters_out, double* stats_out) {
+  if (!s || max_iterations < 0) return IDTO_ERR_INVALID_ARG;
+  const SolverConsts& c = s->sc;
+  const size_t T1 = c.T + 1, B = c.B;
+  if (q_guess) IDTO_CUDA_CHECK(cudaMemcpyAsync(s->bf.st.q, q_guess, B * T1 * c.nq * 8, cudaMemcpyHostToDevice, s->stream));
+  if (q_init) IDTO_CUDA_CHECK(cudaMemcpyAsync(s->q_init, q_init, B * c.nq * 8, cudaMemcpyHostToDevice, s->stream));
+  if (v_init) IDTO_CUDA_CHECK(cudaMemcpyAsync(s->v_init, v_init, B * c.nv * 8, cudaMemcpyHostToDevice, s->stream));
+  if (q_nom) IDTO_CUDA_CHECK(cudaMemcpyAsync(s->q_nom, q_nom, B * T1 * c.nq * 8, cudaMemcpyHostToDevice, s->stream));
+  if (v_nom) IDTO_CUDA_CHECK(cudaMemcpyAsync(s->v_nom, v_nom, B * T1 * c.nv * 8, cudaMemcpyHostToDevice, s->stream));
+  if (q_guess || q_init || v_init || q_nom || v_nom)
+    k_set_ctl<<<(c.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, c.B, 1, 0.0);
+  if (int rc = solve_enqueue(s, max_iterations)) return rc;
+  // solution = {q, EvalV, EvalTau} (cc:2636-2638)
+  enqueue_trajectory(s, false, false);
+  if (q_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(q_out, s->bf.st.q, B * T1 * c.nq * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (v_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(v_out, s->bf.st.v, B * T1 * c.nv * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (tau_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(tau_out, s->bf.st.tau, B * c.T * c.nv * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (stats_out)
+    for (size_t b = 0; b < B; ++b)
+      IDTO_CUDA_CHECK(cudaMemcpyAsync(stats_out + b * max_iterations * IDTO_NUM_STATS,
+                                      s->bf.stats + b * s->bf.stats_cap * IDTO_NUM_STATS,
+                                      size_t(max_iterations) * IDTO_NUM_STATS * 8, cudaMemcpyDeviceToHost, s->stream));
+  (void)iters_out;
+  return IDTO_OK;
+}
+
+int idto_synchronize(idto_solver_t s) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  return check_status(s);
+}
+
+long idto_launch_count(idto_solver_t s) { return s ? g_launch_counter - s->launches0 : IDTO_ERR_INVALID_ARG; }
+
+int idto_profile_enable(idto_solver_t s, int enable) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaStreamSynchronize(s->stream);
+  for (auto& kv : s->prof)
+    for (auto& e : kv.second) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
+  s->prof.clear();
+  s->profile = enable != 0;
+  return IDTO_OK;
+}
+
+int idto_profile_read(idto_solver_t s, const char* kernel, double* total_ms, long* launches) {
+  if (!s || !kernel) return IDTO_ERR_INVALID_ARG;
+  IDTO_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+  double tot = 0.0;
+  long n = 0;
+  auto it = s->prof.find(kernel);
+  if (it != s->prof.end())
+    for (auto& e : it->second) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) tot += ms, ++n;
+    }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  return IDTO_OK;
+}
+
+}  // extern "C"

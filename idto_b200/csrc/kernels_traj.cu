@@ -1,0 +1,178 @@
+// Trajectory-level cache entries: N+(q), v, a (cc:178-202, cc:1633-1647), tau (cc:204-226),
+// cost (cc:136-176) and the equality-constraint violations h (cc:1267-1279).
+#include "dynamics.cuh"
+#include "reduce.cuh"
+
+namespace idto {
+
+// One CTA per problem.  v_t = N+(q_t)(q_t - q_{t-1})/dt, a_t = (v_{t+1} - v_t)/dt.  N+ is the
+// identity pattern (preset at creation) except for the 3x4 quaternion blocks written here.
+__global__ void k_traj(DevModel dm, SolverConsts sc, TrajBuf tb, const double* __restrict__ v_init,
+                       const ProbCtl* __restrict__ ctl, int force) {
+  const int b = blockIdx.x;
+  if (!force && !ctl[b].traj_dirty) return;
+  const int T = sc.T, nq = sc.nq, nv = sc.nv;
+  const double* q = tb.q + size_t(b) * (T + 1) * nq;
+  double* v = tb.v + size_t(b) * (T + 1) * nv;
+  double* a = tb.a + size_t(b) * T * nv;
+  double* Np = tb.Nplus + size_t(b) * (T + 1) * nv * nq;
+  const int* jtype = dm.itab + dm.o_jtype;
+  const int* qs = dm.itab + dm.o_qs;
+  const int* vs = dm.itab + dm.o_vs;
+  for (int idx = threadIdx.x; idx < (T + 1) * dm.nb; idx += blockDim.x) {
+    const int t = idx / dm.nb, k = idx % dm.nb;
+    const int jt = jtype[k], q0 = qs[k], v0 = vs[k];
+    const double* qt = q + size_t(t) * nq + q0;
+    double* vt = v + size_t(t) * nv + v0;
+    if (jt == IDTO_JOINT_QUAT_FLOATING) {
+      V3 col[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        col[c] = quat_nplus_col(qt, c);
+        double* dst = Np + size_t(t) * nv * nq + size_t(q0 + c) * nv + v0;
+        dst[0] = col[c].x, dst[1] = col[c].y, dst[2] = col[c].z;
+      }
+      if (t == 0) {
+        for (int j = 0; j < 6; ++j) vt[j] = v_init[size_t(b) * nv + v0 + j];
+      } else {
+        const double* qm = qt - nq;
+        V3 acc = {0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double d = qt[c] - qm[c];
+          acc.x += col[c].x * d, acc.y += col[c].y * d, acc.z += col[c].z * d;
+        }
+        vt[0] = acc.x / sc.dt, vt[1] = acc.y / sc.dt, vt[2] = acc.z / sc.dt;
+        for (int j = 0; j < 3; ++j) vt[3 + j] = (qt[4 + j] - qm[4 + j]) / sc.dt;
+      }
+    } else {
+      const int n = jt == IDTO_JOINT_PLANAR ? 3 : 1;
+      for (int j = 0; j < n; ++j)
+        vt[j] = t == 0 ? v_init[size_t(b) * nv + v0 + j] : (qt[j] - qt[j - nq]) / sc.dt;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < T * nv; idx += blockDim.x) a[idx] = (v[idx + nv] - v[idx]) / sc.dt;
+}
+
+// tau_t = ID(q_{t+1}, v_{t+1}, a_t): one G-lane group per (b, t).
+template <int G>
+__global__ void __launch_bounds__(128) k_tau(DevModel dm, SolverConsts sc, TrajBuf tb,
+                                             const ProbCtl* __restrict__ ctl, int force) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int* si = reinterpret_cast<int*>(smem);
+  double* sd = reinterpret_cast<double*>(smem + dm.itab_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + dm.itab_bytes + dm.dtab_bytes);
+  double* gbase = reinterpret_cast<double*>(smem + model_smem_bytes(dm));
+  stage_model(dm, si, sd, bar);
+  const SModel M = make_smodel(dm, si, sd);
+  const int groups = blockDim.x / G, grp = threadIdx.x / G, k = threadIdx.x % G;
+  const GroupSmem S = make_group_smem(dm, gbase + size_t(grp) * group_smem_doubles(dm));
+  const int T = sc.T, nq = sc.nq, nv = sc.nv;
+  const int item = blockIdx.x * groups + grp;
+  const bool in_range = item < sc.B * T;
+  const int b = in_range ? item / T : 0, t = in_range ? item % T : 0;
+  const bool live = in_range && (force || ctl[b].traj_dirty);
+  const bool body = k < M.nb;
+  double qb[7] = {1, 0, 0, 0, 0, 0, 0}, vb[6] = {0, 0, 0, 0, 0, 0}, ab[6] = {0, 0, 0, 0, 0, 0}, taub[6];
+  int jt = 0, q0 = 0, v0 = 0;
+  if (body) {
+    jt = M.jtype[k], q0 = M.qs[k], v0 = M.vs[k];
+    const double* q = tb.q + (size_t(b) * (T + 1) + t + 1) * nq + q0;
+    const double* v = tb.v + (size_t(b) * (T + 1) + t + 1) * nv + v0;
+    const double* a = tb.a + (size_t(b) * T + t) * nv + v0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (j < joint_nq(jt)) qb[j] = q[j];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (j < joint_nv(jt)) vb[j] = v[j], ab[j] = a[j];
+  }
+  LaneKin L;
+  PositionPhase<G>(M, S, sc, k, qb, &L);
+  VelocityPhase<G>(M, S, sc, k, L, vb, ab, true, taub);
+  if (live && body) {
+    double* tau = tb.tau + (size_t(b) * T + t) * nv + v0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (j < joint_nv(jt)) tau[j] = taub[j];
+  }
+}
+
+// Cost (cc:148-176, diagonal weights) and h (cc:1274-1278); one CTA per problem.
+__global__ void k_cost(SolverConsts sc, TrajBuf tb, const double* __restrict__ q_nom,
+                       const double* __restrict__ v_nom, ProbCtl* __restrict__ ctl, int force, int clear_flag) {
+  __shared__ double red[32];
+  const int b = blockIdx.x;
+  if (!force && !ctl[b].traj_dirty) return;
+  const int T = sc.T, nq = sc.nq, nv = sc.nv;
+  const double* q = tb.q + size_t(b) * (T + 1) * nq;
+  const double* v = tb.v + size_t(b) * (T + 1) * nv;
+  const double* tau = tb.tau + size_t(b) * T * nv;
+  const double* qn = q_nom + size_t(b) * (T + 1) * nq;
+  const double* vn = v_nom + size_t(b) * (T + 1) * nv;
+  double run = 0.0, term = 0.0;
+  for (int t = threadIdx.x; t <= T; t += blockDim.x) {
+    double cq = 0, cv = 0, cu = 0;
+    for (int i = 0; i < nq; ++i) {
+      const double e = q[t * nq + i] - qn[t * nq + i];
+      cq += e * (t < T ? sc.Qq[i] : sc.Qfq[i]) * e;
+    }
+    for (int i = 0; i < nv; ++i) {
+      const double e = v[t * nv + i] - vn[t * nv + i];
+      cv += e * (t < T ? sc.Qv[i] : sc.Qfv[i]) * e;
+    }
+    if (t < T) {
+      for (int i = 0; i < nv; ++i) cu += tau[t * nv + i] * sc.R[i] * tau[t * nv + i];
+      run += (cq + cv) + cu;
+    } else {
+      term += cq + cv;
+    }
+  }
+  run = block_sum(run, red);
+  term = block_sum(term, red);
+  if (threadIdx.x == 0) tb.cost[b] = run * sc.dt + term;
+  for (int idx = threadIdx.x; idx < sc.nh; idx += blockDim.x) {
+    const int t = idx / sc.nu, j = idx % sc.nu;
+    tb.h[size_t(b) * sc.nh + idx] = tau[t * nv + sc.unact[j]];
+  }
+  if (clear_flag && threadIdx.x == 0) ctl[b].traj_dirty = 0;
+}
+
+template <int G>
+static void launch_tau_g(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl,
+                         bool force, cudaStream_t stream) {
+  const int threads = 128, groups = threads / G;
+  const int smem = model_smem_bytes(dm) + groups * group_smem_doubles(dm) * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_tau<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const int grid = (sc.B * sc.T + groups - 1) / groups;
+  g_launch_counter += 1;
+  k_tau<G><<<grid, threads, smem, stream>>>(dm, sc, tb, ctl, force ? 1 : 0);
+}
+
+void launch_traj(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch, bool force,
+                 cudaStream_t stream) {
+  const TrajBuf& tb = scratch ? bf.sc : bf.st;
+  g_launch_counter += 1;
+  k_traj<<<sc.B, 64, 0, stream>>>(dm, sc, tb, bf.v_init, bf.ctl, force ? 1 : 0);
+}
+
+void launch_tau(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch, bool force,
+                cudaStream_t stream) {
+  const TrajBuf& tb = scratch ? bf.sc : bf.st;
+  switch (dm.group) {
+    case 2: launch_tau_g<2>(dm, sc, tb, bf.ctl, force, stream); break;
+    case 4: launch_tau_g<4>(dm, sc, tb, bf.ctl, force, stream); break;
+    case 8: launch_tau_g<8>(dm, sc, tb, bf.ctl, force, stream); break;
+    case 16: launch_tau_g<16>(dm, sc, tb, bf.ctl, force, stream); break;
+    default: launch_tau_g<32>(dm, sc, tb, bf.ctl, force, stream); break;
+  }
+  g_launch_counter += 1;
+  k_cost<<<sc.B, 64, 0, stream>>>(sc, tb, bf.q_nom, bf.v_nom, bf.ctl, force ? 1 : 0, scratch ? 0 : 1);
+}
+
+}  // namespace idto

@@ -1,0 +1,26 @@
+// Deterministic block reductions (fixed shuffle tree, no atomics).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace idto {
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// All threads of the block must call; `red` is a shared array of >= 32 doubles.  Every thread
+// receives the total.
+__device__ __forceinline__ double block_sum(double x, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  x = warp_sum(x);
+  __syncthreads();  // protect `red` from a previous call
+  if (lane == 0) red[wid] = x;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+}  // namespace idto

@@ -1,0 +1,108 @@
+// Host/device shared declarations of the idto_b200 CUDA layer.
+//
+// Data layout in HBM (all fp64, batch-major; one "problem" = one WarmStart of the reference,
+// optimizer/warm_start.h:23-76).  T = num_steps, n = (T+1)*nq, nh = nu*T.
+//   q     [B][T+1][nq]      v [B][T+1][nv]     a, tau [B][T][nv]     Nplus [B][T+1][nv*nq] (col-major)
+//   dtau_dqm/dqt/dqp [B][T][nv*nq] (col-major nv x nq blocks, inverse_dynamics_partials.h:20-85)
+//   g, D, gs, gm, dq, dqH, pH ... [B][n]
+//   H bands A,B,C (unscaled) and scaled copies [B][T+1][nq*nq] (col-major blocks, lower bands only;
+//     D_i = B_{i+1}^T and E_i = A_{i+2}^T are never materialised)
+//   J~ as three row bands Jm,Jt,Jp [B][T][nu*nq] (row-major nu x nq: the rows of the ID partials of
+//     the unactuated dofs times D), instead of the reference's dense (nu*T) x n matrix
+//   factor: K, Ginv, Y, Z [B][T+1][nq*nq];  X = H~^-1 J~^T [B][nh][n];  S [B][nh*nh]
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/idto_b200.h"
+#include "common.cuh"
+
+namespace idto {
+
+constexpr int kMaxChildren = 8;
+constexpr int kMaxGroup = 32;  // bodies per inverse-dynamics evaluation group (lanes)
+
+// Baked model on the device: two SoA tables (ints, doubles) copied to shared memory by TMA.
+struct DevModel {
+  const int* itab;
+  const double* dtab;
+  int itab_bytes, dtab_bytes;  // multiples of 16
+  int nb, nbp, nq, nv, ng, np, npp, nlevels, group;  // nbp/npp: padded strides; group: lanes per evaluation
+  double gx, gy, gz;
+  // int table offsets (in ints)
+  int o_parent, o_jtype, o_qs, o_vs, o_level, o_nchild, o_child, o_flags, o_qowner, o_gbody, o_gtype, o_pA, o_pB;
+  // double table offsets (in doubles)
+  int o_XPF, o_RMB, o_axis, o_mass, o_com, o_inertia, o_damping, o_gdims, o_XBG;
+};
+
+// Constants of one TrajectoryOptimizer (problem + params), uniform across the batch.
+struct SolverConsts {
+  int B, T, nq, nv, nu, n, nh;
+  double dt;
+  int method, scaling, scaling_method, eq, normalize_quat, check_convergence;
+  double k, sigma, vd, vs, mu, threshold;  // contact (cc:257-269)
+  double Delta_max;
+  double tol[6];
+  const double *Qq, *Qv, *Qfq, *Qfv, *R;  // diagonals, device [nq]/[nv]
+  const int* unact;                       // device [nu]
+  const int* quat_starts;                 // device [nquat]
+  int nquat;
+};
+
+// One TrajectoryOptimizerState's trajectory-level cache (state.h:37-351) for the batch.
+struct TrajBuf {
+  double *q, *v, *a, *tau, *Nplus, *cost, *h;
+};
+
+// Per-problem trust-region control block (device resident; host never reads it mid-solve).
+struct ProbCtl {
+  double Delta, rho, prev_cost, merit, cost_kp, gnorm, hnorm, dq_norm, dqH_norm, q_norm, dL_dq;
+  int traj_dirty;    // q changed: v, a, tau, cost, h stale
+  int derivs_dirty;  // partials / g / H / D / factor / lambda stale
+  int active;        // still iterating (not converged)
+  int tr_active;     // dogleg hit the trust-region boundary
+  int iters;         // iterations recorded so far in this idto_solve call
+  int reason;        // ConvergenceReason bits
+  int pending;       // convergence check of the last accepted step still to be evaluated
+  int pad;
+};
+
+struct SolverBufs {
+  TrajBuf st, sc;  // state, scratch_state
+  const double *q_init, *v_init, *q_nom, *v_nom;
+  double *dqm, *dqt, *dqp;
+  double *g, *D, *gs, *gm, *lambda, *merit;
+  double *HA, *HB, *HC, *SA, *SB, *SC;  // unscaled / scaled lower bands
+  double *Jm, *Jt, *Jp;                 // scaled constraint Jacobian bands
+  double *FK, *FG, *FY, *FZ;            // block-Thomas factor: K_i, G_i^-1, Y_i, Z_i
+  double *X, *S, *rhs;                  // Lagrange multiplier workspace
+  double *pH, *dq, *dqH, *tmp1, *tmp2;
+  double* red;                          // [B][8] reduction scratch (gHg, gg, ...)
+  ProbCtl* ctl;
+  double* stats;  // [B][stats_cap][IDTO_NUM_STATS]
+  int stats_cap;
+  int* status;  // [1] sticky device-side error flag (factorisation failure)
+};
+
+// ---- kernel launchers (each in its own .cu; all asynchronous on `stream`) ---------------------
+void launch_traj(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool scratch, bool force,
+                 cudaStream_t stream);
+void launch_tau(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool scratch, bool force,
+                cudaStream_t stream);
+void launch_partials(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
+                     cudaStream_t stream);
+void launch_assemble(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
+                     cudaStream_t stream);
+void launch_factor(const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
+void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
+                     cudaStream_t stream);
+void launch_conv_check(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
+void launch_clear_dirty(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
+void launch_dogleg(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
+void launch_trust_update(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool commit,
+                         cudaStream_t stream);
+int partials_smem_bytes(const DevModel& dm, int threads);
+extern long g_launch_counter;  // kernels launched by this library (all solvers)
+
+}  // namespace idto

@@ -588,10 +588,13 @@ static bool ldlt_solve(Mat A, Vec* b) {
     const double d = A(k, k);
     if (d == 0.0) continue;
     for (int i = k + 1; i < n; ++i) A(i, k) /= d;
+    // Keep the whole trailing block symmetric-valid (both triangles) so that later symmetric
+    // row/column swaps move correct values.
     for (int j = k + 1; j < n; ++j) {
       const double ljd = A(j, k) * d;
-      for (int i = j; i < n; ++i) A(i, j) -= A(i, k) * ljd;
+      for (int i = k + 1; i < n; ++i) A(i, j) -= A(i, k) * ljd;
     }
+    for (int j = k + 1; j < n; ++j) A(k, j) = A(j, k);
   }
   Vec y(n);
   for (int i = 0; i < n; ++i) y[i] = (*b)[perm[i]];

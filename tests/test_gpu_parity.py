@@ -1,0 +1,156 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, cache entry by cache entry,
+on the same seeded inputs.  Tolerances (fp64):
+  * trajectory level (v, a, tau, cost, h, N+): 1e-11 relative — different summation order / FMA
+    contraction / sincos implementations only;
+  * finite-difference partials: 2e-6 * max(1, |x|, scale) — a 1-ulp difference in tau is amplified by
+    1/dq ~ 6.7e7 (SURVEY.md §7 "Finite-difference conditioning"; the reference's own FD-vs-AD test
+    tolerances are 10..100*sqrt(eps), optimizer/test/trajectory_optimizer_test.cc:256-257);
+  * everything assembled from the partials (g, H, D, J, lambda, dq, rho): stated per assertion.
+"""
+import numpy as np
+import pytest
+
+from idto_b200 import problems
+from idto_b200.types import GRAD_CENTRAL, GRAD_CENTRAL4, GRAD_FORWARD
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b, scale=None):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    if scale is None:
+        scale = max(1.0, float(np.nanmax(np.abs(b))) if b.size else 1.0)
+    mask = ~(np.isnan(a) & np.isnan(b))
+    return float(np.max(np.abs(a - b)[mask]) / scale) if mask.any() else 0.0
+
+
+def make_pair(oracle_mod, name, method, batch=1, **kw):
+    from idto_b200 import capi
+    m, dt, prob, params, guess = getattr(problems, name)(gradients_method=method, **kw)
+    model = capi.Model(m)
+    gs = capi.BatchSolver(model, dt, prob, params, batch)
+    oc = oracle_mod.Oracle(m, dt, prob, params)
+    return m, dt, prob, params, np.array(guess), gs, oc
+
+
+def wiggle(guess, seed, amp=0.05):
+    rng = np.random.default_rng(seed)
+    q = np.array(guess, float).copy()
+    q[1:] += rng.normal(0, amp, q[1:].shape)
+    return q
+
+
+CASES = [("acrobot", {}), ("spinner", {}), ("hopper", {}), ("mini_cheetah", {})]
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+@pytest.mark.parametrize("method", [GRAD_FORWARD, GRAD_CENTRAL, GRAD_CENTRAL4])
+def test_cache_entries_match_oracle(oracle_mod, name, kw, method):
+    m, dt, prob, params, guess, gs, oc = make_pair(oracle_mod, name, method, **kw)
+    q = wiggle(guess, 7, 0.03 if name == "mini_cheetah" else 0.05)
+    gs.set_q(q)
+    oc.set_q(q)
+    gs.eval(4)
+    oc.eval(4)
+    for f in ("Nplus", "v", "a", "tau", "cost", "h"):
+        assert relerr(gs.get(f)[0], oc.get(f)) < 1e-11, f
+    sc = max(1.0, np.nanmax(np.abs(oc.get("dtau_dqp"))))
+    for f in ("dtau_dqm", "dtau_dqt", "dtau_dqp"):
+        assert relerr(gs.get(f)[0], oc.get(f), sc) < 2e-6, f
+    for f, tol in (("g", 2e-6), ("H_A", 4e-6), ("H_B", 4e-6), ("H_C", 4e-6), ("D", 2e-6), ("Hs_A", 4e-6),
+                   ("Hs_B", 4e-6), ("Hs_C", 4e-6), ("gs", 2e-6)):
+        assert relerr(gs.get(f)[0], oc.get(f)) < tol, f
+    if oc.nu > 0 and params.equality_constraints:
+        assert relerr(gs.get("J")[0], oc.get("J")) < 2e-6
+        lam_o = oc.get("lambda")
+        assert relerr(gs.get("lambda")[0], lam_o) < 1e-3, "lambda"  # cond(J H^-1 J^T) * FD noise
+        assert relerr(gs.get("merit")[0], oc.get("merit")) < 1e-6
+    assert relerr(gs.get("gm")[0], oc.get("gm")) < 1e-3
+    assert relerr(gs.get("dqH")[0], oc.get("dqH")) < 1e-3
+    assert relerr(gs.get("dq")[0], oc.get("dq")) < 1e-3
+    assert gs.get("dq_active")[0, 0] == oc.get("dq_active")[0]
+    assert abs(gs.get("rho")[0, 0] - oc.get("rho")[0]) < 1e-3 * max(1.0, abs(oc.get("rho")[0]))
+
+
+def test_contact_pair_indexing_is_exact(oracle_mod):
+    """Contact-pair set per time step must be identical (bit-exact indexing): compare the active-pair
+    masks implied by tau differences with/without contact through the oracle's pair report, on the
+    cheetah standing on the ground (4 foot-ground pairs, ascending registration order)."""
+    m, dt, prob, params, guess, gs, oc = make_pair(oracle_mod, "mini_cheetah", GRAD_CENTRAL)
+    assert list(zip(m.pair_geomA.tolist(), m.pair_geomB.tolist())) == [(0, 1), (0, 2), (0, 3), (0, 4)]
+    assert m.geom_body.tolist() == [-1, 3, 6, 9, 12]
+    q = wiggle(guess, 3, 0.02)
+    gs.set_q(q)
+    oc.set_q(q)
+    gs.eval(0)
+    oc.eval(0)
+    v, a = oc.get("v").reshape(-1, m.nv), oc.get("a").reshape(-1, m.nv)
+    active = np.array([oc.inverse_dynamics(q[t + 1], v[t + 1], a[t])[1] for t in range(prob.num_steps)])
+    assert active.shape == (prob.num_steps, 4) and active.all()  # feet are within the force threshold
+    assert relerr(gs.get("tau")[0], oc.get("tau")) < 1e-11
+
+
+@pytest.mark.parametrize("name,iters,tol", [("spinner", 30, 1e-5), ("hopper", 10, 1e-5), ("acrobot", 20, 1e-5)])
+def test_solve_matches_oracle(oracle_mod, name, iters, tol):
+    """q*, tau*, final cost after `iters` trust-region iterations from identical inputs."""
+    m, dt, prob, params, guess, gs, oc = make_pair(oracle_mod, name, GRAD_CENTRAL)
+    gs.set_q(guess)
+    oc.set_q(guess)
+    it, reason, stats = gs.solve(iters)
+    k, _, so = oc.solve(iters)
+    assert it[0] == k == iters
+    # accept/reject decisions and trust-region radii identical
+    assert np.array_equal(stats[0, :, 1], so[:, 1])
+    assert relerr(stats[0, :, 0], so[:, 0]) < tol
+    q, v, tau = gs.solution()
+    qo, vo, tauo = oc.solution()
+    assert relerr(q[0], qo) < tol and relerr(tau[0], tauo) < 100 * tol
+
+
+def test_spinner_end_to_end_golden_on_gpu(oracle_mod):
+    """python_bindings/test/trajectory_optimizer_test.py:84-85 through the CUDA path (forward
+    differences, 200 iterations): q_T ~= [0.287, 1.497, 1.995] within 1e-3."""
+    m, dt, prob, params, guess, gs, oc = make_pair(oracle_mod, "spinner", GRAD_FORWARD)
+    gs.set_q(guess)
+    it, _, _ = gs.solve(200)
+    q, _, _ = gs.solution()
+    assert it[0] == 200
+    assert np.linalg.norm(q[0, -1] - np.array([0.287, 1.497, 1.995])) < 1e-3
+
+
+def test_batch_elements_are_independent(oracle_mod):
+    """Batch element b must equal a single solve of the same perturbed problem (no cross-talk)."""
+    from idto_b200 import capi
+    m, dt, prob, params, guess = problems.hopper(gradients_method=GRAD_CENTRAL)
+    B = 5
+    q0, v0, qg = problems.perturbed_batch(m, prob, B)
+    model = capi.Model(m)
+    gs = capi.BatchSolver(model, dt, prob, params, B)
+    gs.reset_initial_conditions(q0, v0)
+    gs.set_q(qg)
+    it, _, stats = gs.solve(3)
+    qb, _, _ = gs.solution()
+    for b in (0, 3):
+        one = capi.BatchSolver(model, dt, prob, params, 1)
+        one.reset_initial_conditions(q0[b:b + 1], v0[b:b + 1])
+        one.set_q(qg[b:b + 1])
+        _, _, s1 = one.solve(3)
+        q1, _, _ = one.solution()
+        assert np.array_equal(s1[0], stats[b]) and np.array_equal(q1[0], qb[b])
+
+
+def test_warm_start_equals_one_shot_on_gpu(oracle_mod):
+    """python_bindings/test/warm_start_test.py:165-182 through the C ABI: 10 x solve(1) == solve(10)."""
+    from idto_b200 import capi
+    m, dt, prob, params, guess = problems.spinner(max_iterations=10)
+    model = capi.Model(m)
+    a = capi.BatchSolver(model, dt, prob, params, 1)
+    a.set_q(guess)
+    _, _, sa = a.solve(10)
+    b = capi.BatchSolver(model, dt, prob, params, 1)
+    b.set_q(guess)
+    sb = np.concatenate([b.solve(1)[2][0] for _ in range(10)])
+    qa, va, _ = a.solution()
+    qb, vb, _ = b.solution()
+    assert np.max(np.abs(qa - qb)) < 1e-8 and np.max(np.abs(va - vb)) < 1e-8
+    assert np.max(np.abs(sa[0] - sb)) < 1e-8
