@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py — Gauss-Newton iterations/sec on Mini Cheetah T=40 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            the CUDA path (one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path on the host cores
+
+A "step" is one pass of the hot path over one batch: one trust-region iteration (derivative
+pipeline + penta-diagonal solves + dogleg + trust ratio, optimizer/trajectory_optimizer.cc:2495-2625)
+of each of the `batch` = 64 independent warm-started MPC problems resident on a GPU, i.e. one
+`SolveFromWarmStart(max_iterations=1)` per problem, exactly what the reference's MPC loop issues per
+re-plan (`mpc_iters: 1`).  Every step starts from a state whose caches are stale (as after the MPC
+guess shift), so no step is a cheap "rejected step" replay.
+  value = problems * steps / device time, inputs resident in HBM.
+  e2e   = the same through the public C-ABI call with pinned HOST buffers: per step H2D of the
+          guess + initial conditions and D2H of the solution and stats.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from idto_b200 import problems  # noqa: E402
+from idto_b200.types import GRAD_CENTRAL, GRAD_FORWARD, NUM_STATS  # noqa: E402
+
+BATCH = 64
+T = 40
+METRIC = "Gauss-Newton iters/sec, Mini Cheetah T=40"
+
+
+def workload(method):
+    m, dt, prob, params, guess = problems.mini_cheetah(T=T, gradients_method=method, max_iterations=1)
+    return m, dt, prob, params
+
+
+def b_idp_bytes(nq, nv, T):
+    """Algorithmic bytes of one ID-partials evaluation of one problem."""
+    return 8 * ((T + 1) * (nq + nv) + 2 * T * nv + (T + 1) * nv * nq + 3 * T * nv * nq)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            probe = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True)
+            if probe.returncode != 0 or "not a valid" in (probe.stdout + probe.stderr).lower():
+                self.Q = self.Q.replace("clocks_event_reasons", "clocks_throttle_reasons")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_arm(method, steps, warmup, nprob=BATCH, cores=None):
+    """The reference's CPU path (restated: oracle/idto_oracle.cc — Drake is not installable, so this is
+    'kind: port').  Independent optimizers run on independent host threads (the reference's threading
+    contract), one WarmStart each, OpenMP off inside (every core already has a problem)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle
+    m, dt, prob, params = workload(method)
+    cores = cores or os.cpu_count() or 1
+    nthreads = min(cores, nprob)
+    q0, v0, qg = problems.perturbed_batch(m, prob, nprob)
+    orcs = []
+    for b in range(nprob):
+        o = oracle.Oracle(m, dt, prob, params, num_threads=1)
+        o.reset_initial_conditions(q0[b], v0[b])
+        o.set_q(qg[b])
+        orcs.append(o)
+
+    def one(o):
+        o.set_q(o.get("q"))  # stale caches, like an MPC re-solve
+        return o.solve(1)[0]
+
+    with ThreadPoolExecutor(nthreads) as ex:
+        for _ in range(warmup):
+            list(ex.map(one, orcs))
+        t0 = time.perf_counter()
+        iters = 0
+        for _ in range(steps):
+            iters += sum(ex.map(one, orcs))
+        el = time.perf_counter() - t0
+    return iters / el, el / steps * 1e3, nthreads, f"{nprob} problems x {steps} iteration(s), {nthreads} host threads"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="idto_b200", choices=["idto_b200", "reference"])
+    ap.add_argument("--method", default="central", choices=["central", "forward"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    method = GRAD_CENTRAL if args.method == "central" else GRAD_FORWARD
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+    m, dt, prob, params = workload(method)
+    config = {"workload": f"mini_cheetah trot (floating base + 12 DOF, 4 foot-ground pairs), T={T}, "
+                          f"batch={args.batch} independent MPC re-solves per GPU, 1 iteration per step, "
+                          f"gradients={args.method}_differences, equality_constraints=on, scaling=double_sqrt",
+              "model": "mini_cheetah_with_ground", "nq": m.nq, "nv": m.nv, "T": T, "batch_per_gpu": args.batch,
+              "l2": "per-step working set ~230 MB (X, S, bands, partials) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        val, ms, cores, sample = cpu_arm(method, max(1, min(args.steps, 5)), 1, nprob=args.batch)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "iters/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from idto_b200 import capi
+    if not torch.cuda.is_available() or capi.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.batch
+    model = capi.Model(m)
+    gs = capi.BatchSolver(model, dt, prob, params, B)
+    # batch element b of rank r is problem r*B + b of the global job
+    q0, v0, qg = problems.perturbed_batch(m, prob, B * world)
+    sl = slice(rank * B, (rank + 1) * B)
+    q0, v0, qg = q0[sl], v0[sl], qg[sl]
+    gs.reset_initial_conditions(q0, v0)
+    gs.set_q(qg)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        gs.invalidate()
+        gs.resolve_async(1)  # no host pointers: everything stays in HBM, nothing synchronises
+
+    # ---- device-resident throughput ----------------------------------------------------------
+    for _ in range(warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = gs.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    launches = gs.launch_count() - l0
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers ------------------------------------
+    T1 = T + 1
+    hq = torch.from_numpy(qg.copy()).pin_memory()
+    hq0, hv0 = torch.from_numpy(q0.copy()).pin_memory(), torch.from_numpy(v0.copy()).pin_memory()
+    oq = torch.empty((B, T1, m.nq), dtype=torch.float64).pin_memory()
+    ov = torch.empty((B, T1, m.nv), dtype=torch.float64).pin_memory()
+    ot = torch.empty((B, T, m.nv), dtype=torch.float64).pin_memory()
+    ost = torch.empty((B, 1, NUM_STATS), dtype=torch.float64).pin_memory()
+    h2d = (hq.numel() + hq0.numel() + hv0.numel()) * 8
+    d2h = (oq.numel() + ov.numel() + ot.numel() + ost.numel()) * 8
+
+    def step_e2e():
+        gs.resolve_async(1, q_guess=hq.data_ptr(), q_init=hq0.data_ptr(), v_init=hv0.data_ptr(),
+                         q_out=oq.data_ptr(), v_out=ov.data_ptr(), tau_out=ot.data_ptr(), stats_out=ost.data_ptr())
+        gs.synchronize()
+        hq.copy_(oq)  # the next re-solve starts from the previous solution (MPC warm start)
+
+    for _ in range(warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    el = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(el.item())
+
+    # ---- roofline of the dominant kernel (ID partials), CUDA events on the launching stream --------
+    gs.profile_enable(True)
+    for _ in range(5):
+        step_resident()
+    gs.synchronize()
+    stage_ms = {}
+    for name in ("id_partials", "trajectory", "assemble", "factor", "lagrange", "dogleg", "trajectory_scratch",
+                 "trust_update"):
+        tot, n = gs.profile_read(name)
+        stage_ms[name] = tot / max(n, 1)
+    gs.profile_enable(False)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    algo_bytes = b_idp_bytes(m.nq, m.nv, T) * B
+    achieved = algo_bytes / (stage_ms["id_partials"] * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(f"id_partials_{args.method}")
+    except OSError:
+        pass
+    roofline = {"kernel": "k_partials", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
+                "avg_launch_ms": stage_ms["id_partials"],
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "note": "arithmetic intensity ~50 fp64 flop/B: this kernel is fp64-issue/latency bound, not HBM "
+                        "bound (SURVEY.md §8d); the HBM fraction is reported as BASELINE.json defines it",
+                "stage_ms": stage_ms}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            val, cms, cores, sample = cpu_arm(method, 2, 1, nprob=B)
+            line["cpu_baseline"] = {"value": val, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample,
+                                    "ms_per_step": cms}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,7 @@ def lib():
         L.idto_set_q.argtypes = [H, _D]
         L.idto_reset_initial_conditions.argtypes = [H, _D, _D]
         L.idto_update_nominal_trajectory.argtypes = [H, _D, _D]
+        L.idto_invalidate.argtypes = [H]
         L.idto_set_delta.argtypes = [H, _D]
         L.idto_get_delta.argtypes = [H, _D]
         for f in ("idto_eval_trajectory", "idto_eval_derivatives", "idto_eval_assembly", "idto_eval_dogleg",
@@ -151,6 +152,18 @@ class BatchSolver:
         a = self._arr(qn, (self.B, self.T + 1, self.nq))
         b = self._arr(vn, (self.B, self.T + 1, self.nv))
         _check(lib().idto_update_nominal_trajectory(self.h, _p(a), _p(b)))
+        _check(lib().idto_synchronize(self.h))
+
+    def invalidate(self):
+        _check(lib().idto_invalidate(self.h))
+
+    def resolve_async(self, max_iterations, q_guess=None, q_init=None, v_init=None, q_nom=None, v_nom=None,
+                      q_out=None, v_out=None, tau_out=None, stats_out=None):
+        """End-to-end MPC re-solve: arguments are raw host pointers (ints) of pinned buffers or None."""
+        _check(lib().idto_resolve_async(self.h, int(max_iterations), q_guess, q_init, v_init, q_nom, v_nom, q_out,
+                                        v_out, tau_out, None, stats_out))
+
+    def synchronize(self):
         _check(lib().idto_synchronize(self.h))
 
     def set_delta(self, d):

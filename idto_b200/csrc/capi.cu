@@ -431,8 +431,10 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   alloc(&bf.HA, nH), alloc(&bf.HB, nH), alloc(&bf.HC, nH), alloc(&bf.SA, nH), alloc(&bf.SB, nH), alloc(&bf.SC, nH);
   const size_t nJ = size_t(B) * T * std::max(sc.nu, 1) * nq;
   alloc(&bf.Jm, nJ), alloc(&bf.Jt, nJ), alloc(&bf.Jp, nJ);
-  alloc(&bf.FK, nH), alloc(&bf.FG, nH), alloc(&bf.FY, nH), alloc(&bf.FZ, nH);
-  alloc(&bf.X, sc.eq ? size_t(B) * nh * sc.n : 1), alloc(&bf.S, sc.eq ? size_t(B) * nh * nh : 1);
+  const size_t kbm = size_t(nq) + sc.nu;  // KKT block size
+  bf.FK = bf.FG = bf.S = nullptr;
+  alloc(&bf.FY, size_t(B) * (T + 1) * kbm * kbm), alloc(&bf.FZ, size_t(B) * (T + 1) * kbm * kbm);
+  alloc(&bf.X, size_t(B) * (T + 1) * kbm);
   alloc(&bf.rhs, size_t(B) * nh);
   alloc(&bf.pH, nvar), alloc(&bf.dq, nvar), alloc(&bf.dqH, nvar), alloc(&bf.tmp1, nvar), alloc(&bf.tmp2, nvar);
   alloc(&bf.red, size_t(B) * 8);
@@ -500,6 +502,11 @@ int idto_solver_set_stream(idto_solver_t s, void* stream) {
 int idto_set_q(idto_solver_t s, const double* q) {
   if (!s || !q) return IDTO_ERR_INVALID_ARG;
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->bf.st.q, q, size_t(s->sc.B) * s->sc.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 1, 0.0);
+  return IDTO_OK;
+}
+int idto_invalidate(idto_solver_t s) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
   k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 1, 0.0);
   return IDTO_OK;
 }

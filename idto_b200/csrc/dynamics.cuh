@@ -57,18 +57,6 @@ __device__ __forceinline__ void stage_model(const DevModel& dm, int* si, double*
 }
 
 __host__ __device__ inline int model_smem_bytes(const DevModel& dm) { return dm.itab_bytes + dm.dtab_bytes + 16; }
-// Per-group scratch: kin[24][nbp] + F[6][nbp] + pair[10][npp] doubles.
-__host__ __device__ inline int group_smem_doubles(const DevModel& dm) { return 30 * dm.nbp + 10 * dm.npp; }
-
-struct GroupSmem {
-  double* kin;   // [24][nbp]: R_WB(9) p_WB(3) w(3) v(3) alpha(3) acc(3)
-  double* F;     // [6][nbp]: total spatial force about Bo in W (torque xyz, force xyz)
-  double* pair;  // [10][npp]: nhat(3) p_WC(3) fn_c(1) f_BC(3)
-};
-__device__ __forceinline__ GroupSmem make_group_smem(const DevModel& dm, double* base) {
-  return {base, base + 24 * dm.nbp, base + 30 * dm.nbp};
-}
-
 // ------------------------------------------------------------------ mobilizer maps
 // Rotation matrix of a possibly non-unit quaternion (2/|q|^2 form).
 __device__ __forceinline__ M3 quat_to_R(double w, double x, double y, double z) {
@@ -161,11 +149,28 @@ __device__ __forceinline__ PointDist point_to_box(V3 size, const M3& R_WG, V3 p_
   return {dot(grad_W, p_WQ - p_WN), pn, grad_W};
 }
 
-// ------------------------------------------------------------------ lane state
-struct LaneKin {
-  M3 R_WB, R_WF;
-  V3 p_WB, r;  // r = p_WBo - p_WPo
+// ------------------------------------------------------------------ shared-memory slabs
+// Position data of one evaluation (SoA, body-minor): written by PositionPhase, read-only afterwards.
+// It may be private to a group (perturbed q) or shared by all groups of a (b,t) slot (unperturbed q).
+struct PosSmem {
+  double* R_WB;  // [9][nbp]
+  double* p_WB;  // [3][nbp]
+  double* R_WF;  // [9][nbp]
+  double* pg;    // [7][npp]: nhat(3) p_WC(3) fn_c(1)
 };
+// Velocity-level scratch, always private to the group.
+struct VelSmem {
+  double* wv;  // [12][nbp]: w(3) v(3) alpha(3) acc(3); the total spatial force F(6) aliases alpha/acc
+  double* pf;  // [3][npp]: contact force f_BC of each pair
+};
+__host__ __device__ inline int pos_smem_doubles(const DevModel& dm) { return 21 * dm.nbp + 7 * dm.npp; }
+__host__ __device__ inline int vel_smem_doubles(const DevModel& dm) { return 12 * dm.nbp + 3 * dm.npp; }
+__device__ __forceinline__ PosSmem make_pos_smem(const DevModel& dm, double* base) {
+  return {base, base + 9 * dm.nbp, base + 12 * dm.nbp, base + 21 * dm.nbp};
+}
+__device__ __forceinline__ VelSmem make_vel_smem(const DevModel& dm, double* base) {
+  return {base, base + 12 * dm.nbp};
+}
 
 __device__ __forceinline__ M3 load_R(const double* base, int stride, int k) {
   M3 R;
@@ -179,12 +184,10 @@ __device__ __forceinline__ V3 load_V(const double* base, int stride, int k) {
 __device__ __forceinline__ void store_V(double* base, int stride, int k, V3 v) {
   base[k] = v.x, base[stride + k] = v.y, base[2 * stride + k] = v.z;
 }
-
-// Body pose of geometry g's body from the group's slab (identity for the world).
-__device__ __forceinline__ void body_pose(const GroupSmem& S, int nbp, int body, M3* R, V3* p) {
+__device__ __forceinline__ void body_pose(const PosSmem& P, int nbp, int body, M3* R, V3* p) {
   if (body >= 0) {
-    *R = load_R(S.kin, nbp, body);
-    *p = load_V(S.kin + 9 * nbp, nbp, body);
+    *R = load_R(P.R_WB, nbp, body);
+    *p = load_V(P.p_WB, nbp, body);
   } else {
     *R = identity3();
     *p = {0, 0, 0};
@@ -192,18 +195,19 @@ __device__ __forceinline__ void body_pose(const GroupSmem& S, int nbp, int body,
 }
 
 // Position phase.  All lanes of the warp must call (contains __syncwarp); `k` is the lane's body
-// index inside its group, `G` the group size; bodies with k >= nb idle but help with contact pairs.
-// qb: the lane's own joint positions (up to 7).
+// index inside its group of G lanes; lanes with k >= nb idle but help with contact pairs.
+// qb: the lane's own joint positions (up to 7).  Results go to P.
 template <int G>
-__device__ __forceinline__ void PositionPhase(const SModel& M, const GroupSmem& S, const SolverConsts& sc,
-                                              int k, const double* qb, LaneKin* L) {
+__device__ __forceinline__ void PositionPhase(const SModel& M, const PosSmem& P, const SolverConsts& sc,
+                                              int k, const double* qb) {
   const bool body = k < M.nb;
   const int nbp = M.nbp;
-  int jtype = 0, parent = -1, level = -1;
+  int parent = -1, level = -1;
   M3 R_PB = identity3(), R_PF = identity3();
   V3 p_PB = {0, 0, 0};
   if (body) {
-    jtype = M.jtype[k], parent = M.parent[k], level = M.level[k];
+    const int jtype = M.jtype[k];
+    parent = M.parent[k], level = M.level[k];
     R_PF = load_R(M.XPF, nbp, k);
     const V3 p_PF = load_V(M.XPF + 9 * nbp, nbp, k);
     M3 R_FM = identity3();
@@ -227,28 +231,29 @@ __device__ __forceinline__ void PositionPhase(const SModel& M, const GroupSmem& 
     if (!(M.flags[k] & 1)) R_PB = mul(R_PB, load_R(M.RMB, nbp, k));
     p_PB = p_PF + mul(R_PF, p_FM);
   }
+#pragma unroll 1
   for (int l = 0; l < M.nlevels; ++l) {
     if (body && level == l) {
       M3 R_WP;
       V3 p_WP;
-      body_pose(S, nbp, parent, &R_WP, &p_WP);
-      L->R_WB = mul(R_WP, R_PB);
-      L->r = mul(R_WP, p_PB);
-      L->p_WB = p_WP + L->r;
-      L->R_WF = mul(R_WP, R_PF);
+      body_pose(P, nbp, parent, &R_WP, &p_WP);
+      const M3 R_WB = mul(R_WP, R_PB);
+      const V3 p_WB = p_WP + mul(R_WP, p_PB);
+      const M3 R_WF = mul(R_WP, R_PF);
 #pragma unroll
-      for (int e = 0; e < 9; ++e) S.kin[e * nbp + k] = L->R_WB.m[e];
-      store_V(S.kin + 9 * nbp, nbp, k, L->p_WB);
+      for (int e = 0; e < 9; ++e) P.R_WB[e * nbp + k] = R_WB.m[e], P.R_WF[e * nbp + k] = R_WF.m[e];
+      store_V(P.p_WB, nbp, k, p_WB);
     }
     __syncwarp();
   }
   // Contact geometry (cc:272-320 + the position-only part of the force law, cc:349-359).
+#pragma unroll 1
   for (int ip = k; ip < M.np; ip += G) {
     const int gA = M.pA[ip], gB = M.pB[ip];
     M3 R_WA, R_WBd;
     V3 p_WA, p_WBd;
-    body_pose(S, nbp, M.gbody[gA], &R_WA, &p_WA);
-    body_pose(S, nbp, M.gbody[gB], &R_WBd, &p_WBd);
+    body_pose(P, nbp, M.gbody[gA], &R_WA, &p_WA);
+    body_pose(P, nbp, M.gbody[gB], &R_WBd, &p_WBd);
     const M3 R_WGa = mul(R_WA, load_R(M.XBG, M.ng, gA));
     const V3 p_WGa = p_WA + mul(R_WA, load_V(M.XBG + 9 * M.ng, M.ng, gA));
     const M3 R_WGb = mul(R_WBd, load_R(M.XBG, M.ng, gB));
@@ -275,73 +280,75 @@ __device__ __forceinline__ void PositionPhase(const SModel& M, const GroupSmem& 
       const double exponent = -distance / sc.sigma;  // cc:350-359
       fn_c = exponent >= 37 ? -sc.k * distance : sc.sigma * sc.k * log(1 + exp(exponent));
     }
-    const V3 nhat = -nhat_BA_W;                                               // cc:283
+    const V3 nhat = -nhat_BA_W;                                                          // cc:283
     const V3 p_WC = 0.5 * ((mul(R_WGa, p_ACa) + p_WGa) + (mul(R_WGb, p_BCb) + p_WGb));  // cc:309-316
-    store_V(S.pair, M.npp, ip, nhat);
-    store_V(S.pair + 3 * M.npp, M.npp, ip, p_WC);
-    S.pair[6 * M.npp + ip] = fn_c;
+    store_V(P.pg, M.npp, ip, nhat);
+    store_V(P.pg + 3 * M.npp, M.npp, ip, p_WC);
+    P.pg[6 * M.npp + ip] = fn_c;
   }
   __syncwarp();
 }
 
 // Velocity phase: returns the lane's generalized forces tau_b[0..nv_b).  with_bias=false evaluates
-// M(q) * a only (no gravity, damping, contact or velocity terms; used for the analytic
-// dtau_{t+1}/dq_t of the forward-difference method, cc:556-561).
+// M(q) * a only (no gravity, damping, contact or velocity terms): used for d tau_{t+1}/d q_t =
+// M(q_{t+2}) N+_{t+1} / dt^2 (cc:556-561).
 template <int G>
-__device__ __forceinline__ void VelocityPhase(const SModel& M, const GroupSmem& S, const SolverConsts& sc,
-                                              int k, const LaneKin& L, const double* vb, const double* ab,
+__device__ __forceinline__ void VelocityPhase(const SModel& M, const PosSmem& P, const VelSmem& S,
+                                              const SolverConsts& sc, int k, const double* vb, const double* ab,
                                               bool with_bias, double* tau_b) {
   const bool body = k < M.nb;
   const int nbp = M.nbp;
   int jtype = 0, parent = -1, level = -1;
   V3 axis = {0, 0, 1};
   V3 w = {0, 0, 0}, v = {0, 0, 0}, al = {0, 0, 0}, ac = {0, 0, 0};
-  V3 w_rel = {0, 0, 0}, v_rel = {0, 0, 0}, al_rel = {0, 0, 0}, a_rel = {0, 0, 0};
+  V3 w_rel = {0, 0, 0}, v_rel = {0, 0, 0}, al_rel = {0, 0, 0}, a_rel = {0, 0, 0}, r = {0, 0, 0};
   if (body) {
     jtype = M.jtype[k], parent = M.parent[k], level = M.level[k];
     axis = load_V(M.axis, nbp, k);
+    const M3 R_WF = load_R(P.R_WF, nbp, k);
     V3 wF, vF;
     if (with_bias) {
       hinge_map(jtype, axis, vb, &wF, &vF);
-      w_rel = mul(L.R_WF, wF), v_rel = mul(L.R_WF, vF);
+      w_rel = mul(R_WF, wF), v_rel = mul(R_WF, vF);
     }
     hinge_map(jtype, axis, ab, &wF, &vF);
-    al_rel = mul(L.R_WF, wF), a_rel = mul(L.R_WF, vF);
+    al_rel = mul(R_WF, wF), a_rel = mul(R_WF, vF);
+    if (parent >= 0) r = load_V(P.p_WB, nbp, k) - load_V(P.p_WB, nbp, parent);
   }
+#pragma unroll 1
   for (int l = 0; l < M.nlevels; ++l) {
     if (body && level == l) {
       if (parent >= 0) {
-        const V3 wp = load_V(S.kin + 12 * nbp, nbp, parent), vp = load_V(S.kin + 15 * nbp, nbp, parent);
-        const V3 alp = load_V(S.kin + 18 * nbp, nbp, parent), acp = load_V(S.kin + 21 * nbp, nbp, parent);
+        const V3 wp = load_V(S.wv, nbp, parent), vp = load_V(S.wv + 3 * nbp, nbp, parent);
+        const V3 alp = load_V(S.wv + 6 * nbp, nbp, parent), acp = load_V(S.wv + 9 * nbp, nbp, parent);
         w = wp + w_rel;
-        v = vp + cross(wp, L.r) + v_rel;
+        v = vp + cross(wp, r) + v_rel;
         al = alp + cross(wp, w_rel) + al_rel;
-        ac = acp + cross(alp, L.r) + cross(wp, cross(wp, L.r)) + 2.0 * cross(wp, v_rel) + a_rel;
+        ac = acp + cross(alp, r) + cross(wp, cross(wp, r)) + 2.0 * cross(wp, v_rel) + a_rel;
       } else {
         w = w_rel, v = v_rel, al = al_rel, ac = a_rel;
       }
-      store_V(S.kin + 12 * nbp, nbp, k, w);
-      store_V(S.kin + 15 * nbp, nbp, k, v);
-      store_V(S.kin + 18 * nbp, nbp, k, al);
-      store_V(S.kin + 21 * nbp, nbp, k, ac);
+      store_V(S.wv, nbp, k, w);
+      store_V(S.wv + 3 * nbp, nbp, k, v);
+      store_V(S.wv + 6 * nbp, nbp, k, al);
+      store_V(S.wv + 9 * nbp, nbp, k, ac);
     }
     __syncwarp();
   }
   // Contact forces (velocity-dependent part, cc:322-373), one pair per lane.
   if (with_bias && M.np > 0) {
+#pragma unroll 1
     for (int ip = k; ip < M.np; ip += G) {
-      const double fn_c = S.pair[6 * M.npp + ip];
+      const double fn_c = P.pg[6 * M.npp + ip];
       V3 f_BC = {0, 0, 0};
       if (fn_c > 0.0) {
         const int bA = M.gbody[M.pA[ip]], bB = M.gbody[M.pB[ip]];
-        const V3 nhat = load_V(S.pair, M.npp, ip), p_WC = load_V(S.pair + 3 * M.npp, M.npp, ip);
+        const V3 nhat = load_V(P.pg, M.npp, ip), p_WC = load_V(P.pg + 3 * M.npp, M.npp, ip);
         V3 v_Ac = {0, 0, 0}, v_Bc = {0, 0, 0};
         if (bA >= 0)
-          v_Ac = load_V(S.kin + 15 * nbp, nbp, bA) +
-                 cross(load_V(S.kin + 12 * nbp, nbp, bA), p_WC - load_V(S.kin + 9 * nbp, nbp, bA));
+          v_Ac = load_V(S.wv + 3 * nbp, nbp, bA) + cross(load_V(S.wv, nbp, bA), p_WC - load_V(P.p_WB, nbp, bA));
         if (bB >= 0)
-          v_Bc = load_V(S.kin + 15 * nbp, nbp, bB) +
-                 cross(load_V(S.kin + 12 * nbp, nbp, bB), p_WC - load_V(S.kin + 9 * nbp, nbp, bB));
+          v_Bc = load_V(S.wv + 3 * nbp, nbp, bB) + cross(load_V(S.wv, nbp, bB), p_WC - load_V(P.p_WB, nbp, bB));
         const V3 v_AcBc = v_Bc - v_Ac;
         const double vn = dot(nhat, v_AcBc);
         const V3 vt = v_AcBc - vn * nhat;
@@ -357,26 +364,30 @@ __device__ __forceinline__ void VelocityPhase(const SModel& M, const GroupSmem& 
         const V3 ft_BC = (sc.mu * fn) * that_regularized;
         f_BC = fn * nhat + ft_BC;
       }
-      store_V(S.pair + 7 * M.npp, M.npp, ip, f_BC);
+      store_V(S.pf, M.npp, ip, f_BC);
     }
     __syncwarp();
   }
   V3 Tt = {0, 0, 0}, Tf = {0, 0, 0};
+  V3 p_WB = {0, 0, 0};
   int nchild = 0;
   if (body) {
     // applied forces: gravity (cc:232) + contact in pair order (cc:376-384)
     V3 Ft = {0, 0, 0}, Ff = {0, 0, 0};
     const double m = M.mass[k];
-    const V3 c = mul(L.R_WB, load_V(M.com, nbp, k));
+    const M3 R_WB = load_R(P.R_WB, nbp, k);
+    p_WB = load_V(P.p_WB, nbp, k);
+    const V3 c = mul(R_WB, load_V(M.com, nbp, k));
     if (with_bias) {
       const V3 fg = m * M.g;
       Ft = cross(c, fg), Ff = fg;
+#pragma unroll 1
       for (int ip = 0; ip < M.np; ++ip) {
-        if (S.pair[6 * M.npp + ip] > 0.0) {
+        if (P.pg[6 * M.npp + ip] > 0.0) {
           const int bA = M.gbody[M.pA[ip]], bB = M.gbody[M.pB[ip]];
           if (bA == k || bB == k) {
-            const V3 f = load_V(S.pair + 7 * M.npp, M.npp, ip);
-            const V3 pc = load_V(S.pair + 3 * M.npp, M.npp, ip) - L.p_WB;
+            const V3 f = load_V(S.pf, M.npp, ip);
+            const V3 pc = load_V(P.pg + 3 * M.npp, M.npp, ip) - p_WB;
             if (bA == k) Ft = Ft + cross(pc, -f), Ff = Ff - f;
             if (bB == k) Ft = Ft + cross(pc, f), Ff = Ff + f;
           }
@@ -387,32 +398,37 @@ __device__ __forceinline__ void VelocityPhase(const SModel& M, const GroupSmem& 
     const double* I = M.inertia;
     const M3 IB = {{I[k], I[3 * nbp + k], I[4 * nbp + k], I[3 * nbp + k], I[nbp + k], I[5 * nbp + k],
                     I[4 * nbp + k], I[5 * nbp + k], I[2 * nbp + k]}};
-    const V3 Iw = mul(L.R_WB, mul(IB, tmul(L.R_WB, w)));
-    const V3 Ial = mul(L.R_WB, mul(IB, tmul(L.R_WB, al)));
+    const V3 Iw = mul(R_WB, mul(IB, tmul(R_WB, w)));
+    const V3 Ial = mul(R_WB, mul(IB, tmul(R_WB, al)));
     const V3 f = m * (ac + cross(al, c) + cross(w, cross(w, c)));
     const V3 t = Ial + cross(w, Iw) + m * cross(c, ac);
     Tt = t - Ft, Tf = f - Ff;
-    store_V(S.F, nbp, k, Tt);
-    store_V(S.F + 3 * nbp, nbp, k, Tf);
     nchild = M.nchild[k];
   }
+  __syncwarp();  // every lane is done reading alpha/acc of its parent: F may now alias them
+  if (body) {
+    store_V(S.wv + 6 * nbp, nbp, k, Tt);
+    store_V(S.wv + 9 * nbp, nbp, k, Tf);
+  }
   __syncwarp();
+#pragma unroll 1
   for (int l = M.nlevels - 2; l >= 0; --l) {
     if (body && level == l && nchild > 0) {
       for (int ci = 0; ci < nchild; ++ci) {
         const int c = M.child[ci * nbp + k];
-        const V3 tc = load_V(S.F, nbp, c), fc = load_V(S.F + 3 * nbp, nbp, c);
-        const V3 rc = load_V(S.kin + 9 * nbp, nbp, c) - L.p_WB;
+        const V3 tc = load_V(S.wv + 6 * nbp, nbp, c), fc = load_V(S.wv + 9 * nbp, nbp, c);
+        const V3 rc = load_V(P.p_WB, nbp, c) - p_WB;
         Tt = Tt + tc + cross(rc, fc);
         Tf = Tf + fc;
       }
-      store_V(S.F, nbp, k, Tt);
-      store_V(S.F + 3 * nbp, nbp, k, Tf);
+      store_V(S.wv + 6 * nbp, nbp, k, Tt);
+      store_V(S.wv + 9 * nbp, nbp, k, Tf);
     }
     __syncwarp();
   }
   if (body) {
-    const V3 tF = tmul(L.R_WF, Tt), fF = tmul(L.R_WF, Tf);
+    const M3 R_WF = load_R(P.R_WF, nbp, k);
+    const V3 tF = tmul(R_WF, Tt), fF = tmul(R_WF, Tf);
     switch (jtype) {
       case IDTO_JOINT_REVOLUTE: tau_b[0] = dot(axis, tF); break;
       case IDTO_JOINT_PRISMATIC: tau_b[0] = dot(axis, fF); break;

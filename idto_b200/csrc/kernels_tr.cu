@@ -6,9 +6,6 @@
 
 namespace idto {
 
-void launch_penta_solve(const SolverConsts& sc, const SolverBufs& bf, double* X, int ncols, int mode, bool force,
-                        cudaStream_t stream);
-
 namespace {
 
 // y = H~ x for the symmetric block penta-diagonal matrix given by its lower bands
@@ -43,7 +40,7 @@ __device__ __forceinline__ void penta_matvec(const SolverConsts& sc, const doubl
 
 }  // namespace
 
-// Dogleg part 1: Hg = H~ gm, gHg, g.g, and the right-hand side -gm/Delta of the Gauss-Newton step.
+// Dogleg part 1: Hg = H~ gm, gHg, g.g.
 __global__ void __launch_bounds__(256) k_dogleg_pre(SolverConsts sc, SolverBufs bf) {
   __shared__ double red[32];
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, n = sc.n;
@@ -57,13 +54,12 @@ __global__ void __launch_bounds__(256) k_dogleg_pre(SolverConsts sc, SolverBufs 
   for (int e = tid; e < n; e += nt) gHg += gm[e] * Hg[e], gg += gm[e] * gm[e];
   gHg = block_sum(gHg, red);
   gg = block_sum(gg, red);
-  const double Delta = bf.ctl[b].Delta;
-  double* pH = bf.pH + size_t(b) * n;
-  for (int e = tid; e < n; e += nt) pH[e] = -gm[e] / Delta;  // cc:2139
   if (tid == 0) bf.red[b * 8 + 0] = gHg, bf.red[b * 8 + 1] = gg;
 }
 
-// Dogleg part 2 (after pH = H~^-1 (-gm/Delta)): branch logic, dq, dqH, logging scalars, and the
+// Dogleg part 2: pH = H~^-1(-gm/Delta) = x/Delta with x from k_kkt_solve (cc:2139-2140; the solve is
+// linear in the right-hand side, so x is computed once per derivative update and reused by rejected
+// steps); branch logic, dq, dqH, logging scalars, and the
 // scratch trajectory q + dq (cc:1991-1993).
 __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs bf) {
   __shared__ double red[32];
@@ -80,7 +76,7 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
   // pU = -(g.g / gHg) g / Delta  (cc:2157)
   double pU2 = 0.0, pH2 = 0.0, a = 0.0, bq = 0.0;
   for (int e = tid; e < n; e += nt) {
-    const double pu = -(gg / gHg) * gm[e] / Delta, ph = pH[e];
+    const double pu = -(gg / gHg) * gm[e] / Delta, ph = pH[e] / Delta;
     pU2 += pu * pu, pH2 += ph * ph;
     const double d = ph - pu;
     a += d * d, bq += pu * d;
@@ -108,7 +104,7 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
   const double* q = bf.st.q + size_t(b) * n;
   double* qs = bf.sc.q + size_t(b) * n;
   for (int e = tid; e < n; e += nt) {
-    const double pu = -(gg / gHg) * gm[e] / Delta, ph = pH[e];
+    const double pu = -(gg / gHg) * gm[e] / Delta, ph = pH[e] / Delta;
     double x;
     if (branch == 0)
       x = (Delta / pUn) * pu;
@@ -270,7 +266,6 @@ void launch_clear_dirty(const SolverConsts& sc, const SolverBufs& bf, cudaStream
 void launch_dogleg(const SolverConsts& sc, const SolverBufs& bf, cudaStream_t stream) {
   g_launch_counter += 2;
   k_dogleg_pre<<<sc.B, 256, 0, stream>>>(sc, bf);
-  launch_penta_solve(sc, bf, bf.pH, 1, 0, true, stream);
   k_dogleg_post<<<sc.B, 256, 0, stream>>>(sc, bf);
 }
 

@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(128) k_tau(DevModel dm, SolverConsts sc, TrajB
   stage_model(dm, si, sd, bar);
   const SModel M = make_smodel(dm, si, sd);
   const int groups = blockDim.x / G, grp = threadIdx.x / G, k = threadIdx.x % G;
-  const GroupSmem S = make_group_smem(dm, gbase + size_t(grp) * group_smem_doubles(dm));
+  double* gslab = gbase + size_t(grp) * (pos_smem_doubles(dm) + vel_smem_doubles(dm));
+  const PosSmem P = make_pos_smem(dm, gslab);
+  const VelSmem S = make_vel_smem(dm, gslab + pos_smem_doubles(dm));
   const int T = sc.T, nq = sc.nq, nv = sc.nv;
   const int item = blockIdx.x * groups + grp;
   const bool in_range = item < sc.B * T;
@@ -88,9 +90,9 @@ __global__ void __launch_bounds__(128) k_tau(DevModel dm, SolverConsts sc, TrajB
     for (int j = 0; j < 6; ++j)
       if (j < joint_nv(jt)) vb[j] = v[j], ab[j] = a[j];
   }
-  LaneKin L;
-  PositionPhase<G>(M, S, sc, k, qb, &L);
-  VelocityPhase<G>(M, S, sc, k, L, vb, ab, true, taub);
+
+  PositionPhase<G>(M, P, sc, k, qb);
+  VelocityPhase<G>(M, P, S, sc, k, vb, ab, true, taub);
   if (live && body) {
     double* tau = tb.tau + (size_t(b) * T + t) * nv + v0;
 #pragma unroll
@@ -143,7 +145,7 @@ template <int G>
 static void launch_tau_g(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl,
                          bool force, cudaStream_t stream) {
   const int threads = 128, groups = threads / G;
-  const int smem = model_smem_bytes(dm) + groups * group_smem_doubles(dm) * 8;
+  const int smem = model_smem_bytes(dm) + groups * (pos_smem_doubles(dm) + vel_smem_doubles(dm)) * 8;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_tau<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

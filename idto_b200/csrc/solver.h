@@ -102,7 +102,7 @@ void launch_clear_dirty(const SolverConsts& sc, const SolverBufs& b, cudaStream_
 void launch_dogleg(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
 void launch_trust_update(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool commit,
                          cudaStream_t stream);
-int partials_smem_bytes(const DevModel& dm, int threads);
+int partials_smem_bytes(const DevModel& dm, int nq);
 extern long g_launch_counter;  // kernels launched by this library (all solvers)
 
 }  // namespace idto

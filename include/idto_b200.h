@@ -141,6 +141,9 @@ int idto_solver_set_stream(idto_solver_t s, void* stream);
 
 /* WarmStart::set_q (warm_start.h:55). q: host [batch][(T+1)*nq]. Invalidates all caches. */
 int idto_set_q(idto_solver_t s, const double* q_host);
+/* Marks every cache entry stale without changing q (== WarmStart::set_q(get_q()); what an MPC
+ * re-solve does after shifting its guess, examples/mpc_controller.cc:56-59). */
+int idto_invalidate(idto_solver_t s);
 /* ResetInitialConditions (trajectory_optimizer.h:463-468): host [batch][nq], [batch][nv]. */
 int idto_reset_initial_conditions(idto_solver_t s, const double* q_init, const double* v_init);
 /* UpdateNominalTrajectory (trajectory_optimizer.h:477-483): host [batch][(T+1)*nq], [batch][(T+1)*nv]. */

@@ -66,8 +66,20 @@ def test_cache_entries_match_oracle(oracle_mod, name, kw, method):
         assert relerr(gs.get("lambda")[0], lam_o) < 1e-3, "lambda"  # cond(J H^-1 J^T) * FD noise
         assert relerr(gs.get("merit")[0], oc.get("merit")) < 1e-6
     assert relerr(gs.get("gm")[0], oc.get("gm")) < 1e-3
-    assert relerr(gs.get("dqH")[0], oc.get("dqH")) < 1e-3
-    assert relerr(gs.get("dq")[0], oc.get("dq")) < 1e-3
+    # The Gauss-Newton step amplifies the FD noise of the partials by cond(H~): compare loosely with
+    # the oracle, and tightly against the GPU's own linear system H~ (dqH/Delta-scaled) = -gm.
+    assert relerr(gs.get("dqH")[0], oc.get("dqH")) < 2e-2
+    assert relerr(gs.get("dq")[0], oc.get("dq")) < 2e-2
+    nq, nblk = m.nq, prob.num_steps + 1
+    A, Bb, C = (gs.get(f)[0].reshape(nblk, nq, nq).transpose(0, 2, 1) for f in ("Hs_A", "Hs_B", "Hs_C"))
+    x = gs.get("dqH")[0].reshape(nblk, nq)
+    y = np.einsum("irc,ic->ir", C, x)
+    y[1:] += np.einsum("irc,ic->ir", Bb[1:], x[:-1])
+    y[2:] += np.einsum("irc,ic->ir", A[2:], x[:-2])
+    y[:-1] += np.einsum("icr,ic->ir", Bb[1:], x[1:])
+    y[:-2] += np.einsum("icr,ic->ir", A[2:], x[2:])
+    gm = gs.get("gm")[0].reshape(nblk, nq)
+    assert np.max(np.abs(y + gm)) < 1e-9 * max(1.0, np.max(np.abs(gm))) * max(1.0, np.max(np.abs(x)))
     assert gs.get("dq_active")[0, 0] == oc.get("dq_active")[0]
     assert abs(gs.get("rho")[0, 0] - oc.get("rho")[0]) < 1e-3 * max(1.0, abs(oc.get("rho")[0]))
 
