@@ -166,8 +166,9 @@ def main():
     model = capi.Model(m)
     gs = capi.BatchSolver(model, dt, prob, params, B)
     # batch element b of rank r is problem r*B + b of the global job
+    from idto_b200.sharding import shard_slice
     q0, v0, qg = problems.perturbed_batch(m, prob, B * world)
-    sl = slice(rank * B, (rank + 1) * B)
+    sl = shard_slice(B * world, rank, world)  # contiguous slice; no data-path collective
     q0, v0, qg = q0[sl], v0[sl], qg[sl]
     gs.reset_initial_conditions(q0, v0)
     gs.set_q(qg)

@@ -713,11 +713,17 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
   if (q_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(q_out, s->bf.st.q, B * T1 * c.nq * 8, cudaMemcpyDeviceToHost, s->stream));
   if (v_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(v_out, s->bf.st.v, B * T1 * c.nv * 8, cudaMemcpyDeviceToHost, s->stream));
   if (tau_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(tau_out, s->bf.st.tau, B * c.T * c.nv * 8, cudaMemcpyDeviceToHost, s->stream));
-  if (stats_out)
-    for (size_t b = 0; b < B; ++b)
-      IDTO_CUDA_CHECK(cudaMemcpyAsync(stats_out + b * max_iterations * IDTO_NUM_STATS,
-                                      s->bf.stats + b * s->bf.stats_cap * IDTO_NUM_STATS,
-                                      size_t(max_iterations) * IDTO_NUM_STATS * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (stats_out) {
+    if (size_t(max_iterations) == s->stats_cap) {  // contiguous: one copy
+      IDTO_CUDA_CHECK(cudaMemcpyAsync(stats_out, s->bf.stats, B * size_t(max_iterations) * IDTO_NUM_STATS * 8,
+                                      cudaMemcpyDeviceToHost, s->stream));
+    } else {
+      IDTO_CUDA_CHECK(cudaMemcpy2DAsync(stats_out, size_t(max_iterations) * IDTO_NUM_STATS * 8, s->bf.stats,
+                                        s->bf.stats_cap * IDTO_NUM_STATS * 8,
+                                        size_t(max_iterations) * IDTO_NUM_STATS * 8, B, cudaMemcpyDeviceToHost,
+                                        s->stream));
+    }
+  }
   (void)iters_out;
   return IDTO_OK;
 }

@@ -35,3 +35,32 @@ el = time.perf_counter() - t0
 names = ("trajectory", "id_partials", "assemble", "lagrange", "dogleg", "trajectory_scratch", "trust_update")
 print(f"{steps} steps, batch {B}: {el / steps * 1e3:.3f} ms/step wall;",
       {n: round(gs.profile_read(n)[0] / max(gs.profile_read(n)[1], 1), 4) for n in names})
+
+# ---- end-to-end step (pinned host buffers through idto_resolve_async), with a host-side breakdown ----
+try:
+    import torch
+    from idto_b200.types import NUM_STATS
+    T, T1 = 40, 41
+    hq = torch.from_numpy(qg.copy()).pin_memory()
+    hq0, hv0 = torch.from_numpy(q0.copy()).pin_memory(), torch.from_numpy(v0.copy()).pin_memory()
+    oq = torch.empty((B, T1, m.nq), dtype=torch.float64).pin_memory()
+    ov = torch.empty((B, T1, m.nv), dtype=torch.float64).pin_memory()
+    ot = torch.empty((B, T, m.nv), dtype=torch.float64).pin_memory()
+    ost = torch.empty((B, 1, NUM_STATS), dtype=torch.float64).pin_memory()
+    gs.profile_enable(False)
+    tt = [0.0, 0.0, 0.0]
+    for it in range(steps + 3):
+        a = time.perf_counter()
+        gs.resolve_async(1, q_guess=hq.data_ptr(), q_init=hq0.data_ptr(), v_init=hv0.data_ptr(),
+                         q_out=oq.data_ptr(), v_out=ov.data_ptr(), tau_out=ot.data_ptr(), stats_out=ost.data_ptr())
+        b_ = time.perf_counter()
+        gs.synchronize()
+        c = time.perf_counter()
+        hq.copy_(oq)
+        d = time.perf_counter()
+        if it >= 3:
+            tt[0] += b_ - a; tt[1] += c - b_; tt[2] += d - c
+    print("e2e per step [ms]: enqueue %.3f  wait %.3f  host copy %.3f" % tuple(x / steps * 1e3 for x in tt),
+          "rho", float(ost[0, 0, 5]), "cost", float(ost[0, 0, 0]))
+except ImportError:
+    pass
