@@ -193,6 +193,16 @@ class BakedModel:
         with open(path, "w") as f:
             json.dump(self.to_json(), f)
 
+    def save_txt(self, path):
+        """Whitespace-separated table dump read by include/idto_b200.hpp (MultibodyPlant::LoadBaked)."""
+        with open(path, "w") as f:
+            f.write(f"{self.nbodies} {self.nq} {self.nv} {self.ngeoms} {self.npairs}\n")
+            for k in ("parent", "joint_type", "q_start", "v_start", "actuated", "geom_body", "geom_type",
+                      "pair_geomA", "pair_geomB"):
+                f.write(" ".join(str(int(x)) for x in np.asarray(getattr(self, k)).reshape(-1)) + "\n")
+            for k in ("X_PF", "R_MB", "axis", "damping", "mass", "com", "inertia", "gravity", "geom_dims", "X_BG"):
+                f.write(" ".join(repr(float(x)) for x in np.asarray(getattr(self, k), float).reshape(-1)) + "\n")
+
     @classmethod
     def load(cls, path):
         with open(path) as f:

@@ -56,6 +56,7 @@ def lib():
                                          ctypes.POINTER(H)]
         L.idto_solver_destroy.argtypes = [H]
         L.idto_solver_set_stream.argtypes = [H, ctypes.c_void_p]
+        L.idto_solver_set_substreams.argtypes = [H, ctypes.c_int]
         L.idto_set_q.argtypes = [H, _D]
         L.idto_reset_initial_conditions.argtypes = [H, _D, _D]
         L.idto_update_nominal_trajectory.argtypes = [H, _D, _D]
@@ -70,6 +71,8 @@ def lib():
         L.idto_get.argtypes = [H, ctypes.c_char_p, _D]
         L.idto_solve.argtypes = [H, ctypes.c_int, _I, _I, _D]
         L.idto_resolve_async.argtypes = [H, ctypes.c_int] + [ctypes.c_void_p] * 8 + [_I, ctypes.c_void_p]
+        L.idto_fence.argtypes = [H]
+        L.idto_flush_l2.argtypes = [H, ctypes.c_void_p, ctypes.c_size_t]
         L.idto_launch_count.argtypes = [H]
         L.idto_launch_count.restype = ctypes.c_long
         L.idto_profile_enable.argtypes = [H, ctypes.c_int]
@@ -154,6 +157,9 @@ class BatchSolver:
         _check(lib().idto_update_nominal_trajectory(self.h, _p(a), _p(b)))
         _check(lib().idto_synchronize(self.h))
 
+    def set_substreams(self, n):
+        _check(lib().idto_solver_set_substreams(self.h, int(n)))
+
     def invalidate(self):
         _check(lib().idto_invalidate(self.h))
 
@@ -162,6 +168,12 @@ class BatchSolver:
         """End-to-end MPC re-solve: arguments are raw host pointers (ints) of pinned buffers or None."""
         _check(lib().idto_resolve_async(self.h, int(max_iterations), q_guess, q_init, v_init, q_nom, v_nom, q_out,
                                         v_out, tau_out, None, stats_out))
+
+    def fence(self):
+        _check(lib().idto_fence(self.h))
+
+    def flush_l2(self, ptr, nbytes):
+        _check(lib().idto_flush_l2(self.h, ptr, nbytes))
 
     def synchronize(self):
         _check(lib().idto_synchronize(self.h))

@@ -3,6 +3,7 @@
 // one returns IDTO_ERR_NO_DEVICE.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -68,6 +69,13 @@ struct idto_solver_s {
   std::map<std::string, std::vector<ProfEvent>> prof;
   std::vector<ProbCtl> ctl_host;
   size_t stats_cap = 0;
+  // sub-batches on their own streams: the latency-bound per-problem kernels (KKT sweep, TR scalars)
+  // of one sub-batch overlap with the throughput-bound kernels (ID partials, assembly) of another
+  int nsub = 1;
+  std::vector<cudaStream_t> sub_streams;
+  std::vector<cudaEvent_t> sub_done;
+  cudaEvent_t ev_start = nullptr;
+  bool main_dirty = false, subs_dirty = false;
 };
 
 namespace {
@@ -146,6 +154,99 @@ void enqueue_iteration(idto_solver_s* s) {
   }
 }
 
+// View of the solver restricted to problems [b0, b0+nb): every buffer is batch-major.
+void make_view(const idto_solver_s* s, int b0, int nb, SolverConsts* scv, SolverBufs* bfv) {
+  const SolverConsts& c = s->sc;
+  *scv = c;
+  scv->B = nb;
+  SolverBufs v = s->bf;
+  const size_t T = c.T, T1 = c.T + 1, nq = c.nq, nv = c.nv, n = c.n, nh = std::max(c.nh, 1), o = size_t(b0);
+  const size_t kb = nq + c.nu, nuq = size_t(std::max(c.nu, 1)) * nq;
+  for (TrajBuf* tb : {&v.st, &v.sc}) {
+    tb->q += o * T1 * nq, tb->v += o * T1 * nv, tb->a += o * T * nv, tb->tau += o * T * nv;
+    tb->Nplus += o * T1 * nv * nq, tb->cost += o, tb->h += o * nh;
+  }
+  v.q_init += o * nq, v.v_init += o * nv, v.q_nom += o * T1 * nq, v.v_nom += o * T1 * nv;
+  v.dqm += o * T * nv * nq, v.dqt += o * T * nv * nq, v.dqp += o * T * nv * nq;
+  v.g += o * n, v.D += o * n, v.gs += o * n, v.gm += o * n, v.lambda += o * nh, v.merit += o;
+  for (double** p : {&v.HA, &v.HB, &v.HC, &v.SA, &v.SB, &v.SC}) *p += o * T1 * nq * nq;
+  v.Jm += o * T * nuq, v.Jt += o * T * nuq, v.Jp += o * T * nuq;
+  v.FY += o * T1 * kb * kb, v.FZ += o * T1 * kb * kb, v.X += o * T1 * kb, v.rhs += o * nh;
+  v.pH += o * n, v.dq += o * n, v.dqH += o * n, v.tmp1 += o * n, v.tmp2 += o * n, v.red += o * 8;
+  v.ctl += o;
+  if (v.stats) v.stats += o * size_t(v.stats_cap) * IDTO_NUM_STATS;
+  *bfv = v;
+}
+
+// ---- sub-batch streams ------------------------------------------------------------------------------
+// With nsub > 1 the batch is cut into contiguous sub-batches, each with its own stream.  A sub-batch's
+// whole iteration sequence lives on its stream, so consecutive re-solves of different sub-batches
+// pipeline: the sequential KKT sweep of one sub-batch (one CTA per problem, latency bound) overlaps with
+// the ID-partials / assembly kernels of the others.  The caller's stream only forks (after host copies)
+// and joins (before anything the host reads).
+struct Part {
+  SolverConsts sc;
+  SolverBufs bf;
+  cudaStream_t st;
+  int b0;
+};
+bool multi(const idto_solver_s* s) { return s->nsub > 1 && !s->profile; }
+std::vector<Part> make_parts(const idto_solver_s* s) {
+  std::vector<Part> parts(s->nsub);
+  for (int i = 0; i < s->nsub; ++i) {
+    const int b0 = int(size_t(s->sc.B) * i / s->nsub), b1 = int(size_t(s->sc.B) * (i + 1) / s->nsub);
+    make_view(s, b0, b1 - b0, &parts[i].sc, &parts[i].bf);
+    parts[i].st = s->sub_streams[i];
+    parts[i].b0 = b0;
+  }
+  return parts;
+}
+// Before enqueuing on the caller's stream: join the sub-streams.
+void use_main(idto_solver_s* s) {
+  if (s->subs_dirty) {
+    for (int i = 0; i < s->nsub; ++i) {
+      cudaEventRecord(s->sub_done[i], s->sub_streams[i]);
+      cudaStreamWaitEvent(s->stream, s->sub_done[i], 0);
+    }
+    s->subs_dirty = false;
+  }
+  s->main_dirty = true;
+}
+// Before enqueuing on the sub-streams: they wait for what is already on the caller's stream.
+void use_subs(idto_solver_s* s) {
+  if (s->main_dirty) {
+    cudaEventRecord(s->ev_start, s->stream);
+    for (int i = 0; i < s->nsub; ++i) cudaStreamWaitEvent(s->sub_streams[i], s->ev_start, 0);
+    s->main_dirty = false;
+  }
+  s->subs_dirty = true;
+}
+
+__global__ void k_set_ctl(ProbCtl* ctl, int B, int what, double Delta0);
+__global__ void k_set_prev_cost(ProbCtl* ctl, const double* cost, int B);
+
+// `count` trust-region iterations on the sub-streams, stage-major so that earlier sub-batches get the
+// SMs first at every stage (their KKT sweeps then start while later sub-batches still differentiate).
+void enqueue_iterations_parts(idto_solver_s* s, const std::vector<Part>& P, int count) {
+  const DevModel& dm = s->model->dm;
+  for (int k = 0; k < count; ++k) {
+    for (const Part& p : P) {
+      launch_traj(dm, p.sc, p.bf, false, false, p.st);
+      launch_tau(dm, p.sc, p.bf, false, false, p.st);
+    }
+    for (const Part& p : P) launch_partials(dm, p.sc, p.bf, false, p.st);
+    for (const Part& p : P) launch_assemble(dm, p.sc, p.bf, false, p.st);
+    for (const Part& p : P) launch_lagrange(dm, p.sc, p.bf, false, p.st);
+    for (const Part& p : P) {
+      if (s->sc.check_convergence) launch_conv_check(p.sc, p.bf, p.st);
+      launch_dogleg(p.sc, p.bf, p.st);
+      launch_traj(dm, p.sc, p.bf, true, true, p.st);
+      launch_tau(dm, p.sc, p.bf, true, true, p.st);
+      launch_trust_update(dm, p.sc, p.bf, true, p.st);
+    }
+  }
+}
+
 __global__ void k_set_ctl(ProbCtl* ctl, int B, int what, double Delta0) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -199,6 +300,7 @@ int ensure_stats(idto_solver_s* s, size_t cap) {
 }
 
 int check_status(idto_solver_s* s) {
+  use_main(s);
   int st = 0;
   IDTO_CUDA_CHECK(cudaMemcpyAsync(&st, s->bf.status, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   IDTO_CUDA_CHECK(cudaStreamSynchronize(s->stream));
@@ -479,17 +581,47 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   }
   s->ctl_host.resize(B);
   s->launches0 = g_launch_counter;
+  cudaEventCreateWithFlags(&s->ev_start, cudaEventDisableTiming);
+  {
+    int nsub = B >= 32 ? 4 : 1;
+    if (const char* e = std::getenv("IDTO_SUBSTREAMS")) nsub = std::max(1, std::atoi(e));
+    idto_solver_set_substreams(s, nsub);
+  }
   *out = s;
   return IDTO_OK;
 }
 
 int idto_solver_destroy(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  use_main(s);
   cudaDeviceSynchronize();
+  for (auto st : s->sub_streams) cudaStreamDestroy(st);
+  for (auto ev : s->sub_done) cudaEventDestroy(ev);
+  if (s->ev_start) cudaEventDestroy(s->ev_start);
   for (auto& kv : s->prof)
     for (auto& e : kv.second) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
   s->mem.release();
   delete s;
+  return IDTO_OK;
+}
+
+int idto_solver_set_substreams(idto_solver_t s, int n) {
+  if (!s || n < 1 || n > 16) return IDTO_ERR_INVALID_ARG;
+  if (n > s->sc.B) n = s->sc.B;
+  use_main(s);
+  cudaStreamSynchronize(s->stream);
+  for (auto st : s->sub_streams) cudaStreamDestroy(st);
+  for (auto ev : s->sub_done) cudaEventDestroy(ev);
+  s->sub_streams.clear(), s->sub_done.clear();
+  s->nsub = n;
+  if (n > 1)
+    for (int i = 0; i < n; ++i) {
+      cudaStream_t st;
+      cudaEvent_t ev;
+      IDTO_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      IDTO_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      s->sub_streams.push_back(st), s->sub_done.push_back(ev);
+    }
   return IDTO_OK;
 }
 
@@ -501,17 +633,25 @@ int idto_solver_set_stream(idto_solver_t s, void* stream) {
 
 int idto_set_q(idto_solver_t s, const double* q) {
   if (!s || !q) return IDTO_ERR_INVALID_ARG;
+  use_main(s);
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->bf.st.q, q, size_t(s->sc.B) * s->sc.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 1, 0.0);
   return IDTO_OK;
 }
 int idto_invalidate(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  if (multi(s)) {
+    use_subs(s);
+    for (const Part& p : make_parts(s)) k_set_ctl<<<(p.sc.B + 127) / 128, 128, 0, p.st>>>(p.bf.ctl, p.sc.B, 1, 0.0);
+    return IDTO_OK;
+  }
+  use_main(s);
   k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 1, 0.0);
   return IDTO_OK;
 }
 int idto_reset_initial_conditions(idto_solver_t s, const double* q0, const double* v0) {
   if (!s || !q0 || !v0) return IDTO_ERR_INVALID_ARG;
+  use_main(s);
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->q_init, q0, size_t(s->sc.B) * s->sc.nq * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->v_init, v0, size_t(s->sc.B) * s->sc.nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 1, 0.0);
@@ -519,6 +659,7 @@ int idto_reset_initial_conditions(idto_solver_t s, const double* q0, const doubl
 }
 int idto_update_nominal_trajectory(idto_solver_t s, const double* qn, const double* vn) {
   if (!s || !qn || !vn) return IDTO_ERR_INVALID_ARG;
+  use_main(s);
   const size_t T1 = s->sc.T + 1;
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->q_nom, qn, size_t(s->sc.B) * T1 * s->sc.nq * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->v_nom, vn, size_t(s->sc.B) * T1 * s->sc.nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
@@ -527,6 +668,7 @@ int idto_update_nominal_trajectory(idto_solver_t s, const double* qn, const doub
 }
 int idto_set_delta(idto_solver_t s, const double* delta) {
   if (!s || !delta) return IDTO_ERR_INVALID_ARG;
+  use_main(s);
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->bf.red, delta, s->sc.B * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   k_set_delta<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->bf.red, s->sc.B);
   return IDTO_OK;
@@ -535,17 +677,20 @@ int idto_get_delta(idto_solver_t s, double* delta) { return idto_get(s, "delta",
 
 int idto_eval_trajectory(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  use_main(s);
   enqueue_trajectory(s, false, false);
   return check_status(s);
 }
 int idto_eval_derivatives(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  use_main(s);
   enqueue_trajectory(s, false, false);
   enqueue_derivatives(s, false);
   return check_status(s);
 }
 int idto_eval_assembly(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  use_main(s);
   enqueue_trajectory(s, false, false);
   enqueue_derivatives(s, false);
   enqueue_assembly(s, false);
@@ -592,6 +737,7 @@ int idto_get(idto_solver_t s, const char* field, double* out) {
   const SolverConsts& c = s->sc;
   const SolverBufs& bf = s->bf;
   const std::string f(field);
+  use_main(s);
   IDTO_CUDA_CHECK(cudaStreamSynchronize(s->stream));
   const double* src = nullptr;
   if (f == "q") src = bf.st.q;
@@ -653,6 +799,32 @@ int idto_get(idto_solver_t s, const char* field, double* out) {
 
 static int solve_enqueue(idto_solver_t s, int max_iterations) {
   if (int rc = ensure_stats(s, size_t(max_iterations))) return rc;
+  if (multi(s)) {
+    use_subs(s);
+    const std::vector<Part> P = make_parts(s);
+    const DevModel& dm = s->model->dm;
+    for (const Part& p : P) {
+      k_set_ctl<<<(p.sc.B + 127) / 128, 128, 0, p.st>>>(p.bf.ctl, p.sc.B, 2, 0.0);
+      if (s->sc.check_convergence) {  // previous_cost = EvalCost(state) (cc:2494)
+        launch_traj(dm, p.sc, p.bf, false, false, p.st);
+        launch_tau(dm, p.sc, p.bf, false, false, p.st);
+        k_set_prev_cost<<<(p.sc.B + 127) / 128, 128, 0, p.st>>>(p.bf.ctl, p.bf.st.cost, p.sc.B);
+      }
+    }
+    enqueue_iterations_parts(s, P, max_iterations);
+    if (s->sc.check_convergence)
+      for (const Part& p : P) {  // the check of the last accepted step (cc:2604, 2673)
+        launch_traj(dm, p.sc, p.bf, false, false, p.st);
+        launch_tau(dm, p.sc, p.bf, false, false, p.st);
+        launch_partials(dm, p.sc, p.bf, false, p.st);
+        launch_assemble(dm, p.sc, p.bf, false, p.st);
+        launch_lagrange(dm, p.sc, p.bf, false, p.st);
+        launch_conv_check(p.sc, p.bf, p.st);
+        launch_clear_dirty(p.sc, p.bf, p.st);
+      }
+    return IDTO_OK;
+  }
+  use_main(s);
   k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 2, 0.0);
   if (s->sc.check_convergence) {
     // previous_cost = EvalCost(state) (cc:2494)
@@ -700,6 +872,39 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
   if (!s || max_iterations < 0) return IDTO_ERR_INVALID_ARG;
   const SolverConsts& c = s->sc;
   const size_t T1 = c.T + 1, B = c.B;
+  if (multi(s)) {
+    // every sub-batch moves its own slice of the host buffers on its own stream: copies of one
+    // sub-batch overlap with the kernels of the others, and nothing touches the caller's stream
+    if (int rc = ensure_stats(s, size_t(max_iterations))) return rc;
+    use_subs(s);
+    const bool dirty = q_guess || q_init || v_init || q_nom || v_nom;
+    for (const Part& p : make_parts(s)) {
+      const size_t o = size_t(p.b0), nb = size_t(p.sc.B);
+      if (q_guess) IDTO_CUDA_CHECK(cudaMemcpyAsync(p.bf.st.q, q_guess + o * T1 * c.nq, nb * T1 * c.nq * 8, cudaMemcpyHostToDevice, p.st));
+      if (q_init) IDTO_CUDA_CHECK(cudaMemcpyAsync(const_cast<double*>(p.bf.q_init), q_init + o * c.nq, nb * c.nq * 8, cudaMemcpyHostToDevice, p.st));
+      if (v_init) IDTO_CUDA_CHECK(cudaMemcpyAsync(const_cast<double*>(p.bf.v_init), v_init + o * c.nv, nb * c.nv * 8, cudaMemcpyHostToDevice, p.st));
+      if (q_nom) IDTO_CUDA_CHECK(cudaMemcpyAsync(const_cast<double*>(p.bf.q_nom), q_nom + o * T1 * c.nq, nb * T1 * c.nq * 8, cudaMemcpyHostToDevice, p.st));
+      if (v_nom) IDTO_CUDA_CHECK(cudaMemcpyAsync(const_cast<double*>(p.bf.v_nom), v_nom + o * T1 * c.nv, nb * T1 * c.nv * 8, cudaMemcpyHostToDevice, p.st));
+      if (dirty) k_set_ctl<<<(p.sc.B + 127) / 128, 128, 0, p.st>>>(p.bf.ctl, p.sc.B, 1, 0.0);
+    }
+    if (int rc = solve_enqueue(s, max_iterations)) return rc;
+    for (const Part& p : make_parts(s)) {
+      const size_t o = size_t(p.b0), nb = size_t(p.sc.B);
+      launch_traj(s->model->dm, p.sc, p.bf, false, false, p.st);  // solution = {q, EvalV, EvalTau}
+      launch_tau(s->model->dm, p.sc, p.bf, false, false, p.st);
+      if (q_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(q_out + o * T1 * c.nq, p.bf.st.q, nb * T1 * c.nq * 8, cudaMemcpyDeviceToHost, p.st));
+      if (v_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(v_out + o * T1 * c.nv, p.bf.st.v, nb * T1 * c.nv * 8, cudaMemcpyDeviceToHost, p.st));
+      if (tau_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(tau_out + o * c.T * c.nv, p.bf.st.tau, nb * c.T * c.nv * 8, cudaMemcpyDeviceToHost, p.st));
+      if (stats_out)
+        IDTO_CUDA_CHECK(cudaMemcpy2DAsync(stats_out + o * max_iterations * IDTO_NUM_STATS,
+                                          size_t(max_iterations) * IDTO_NUM_STATS * 8, p.bf.stats,
+                                          s->bf.stats_cap * IDTO_NUM_STATS * 8,
+                                          size_t(max_iterations) * IDTO_NUM_STATS * 8, nb, cudaMemcpyDeviceToHost, p.st));
+    }
+    (void)iters_out;
+    return IDTO_OK;
+  }
+  use_main(s);
   if (q_guess) IDTO_CUDA_CHECK(cudaMemcpyAsync(s->bf.st.q, q_guess, B * T1 * c.nq * 8, cudaMemcpyHostToDevice, s->stream));
   if (q_init) IDTO_CUDA_CHECK(cudaMemcpyAsync(s->q_init, q_init, B * c.nq * 8, cudaMemcpyHostToDevice, s->stream));
   if (v_init) IDTO_CUDA_CHECK(cudaMemcpyAsync(s->v_init, v_init, B * c.nv * 8, cudaMemcpyHostToDevice, s->stream));
@@ -728,8 +933,29 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
   return IDTO_OK;
 }
 
+int idto_fence(idto_solver_t s) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  use_main(s);  // joins the sub-streams into the caller's stream; later sub-stream work forks after it
+  return IDTO_OK;
+}
+
+int idto_flush_l2(idto_solver_t s, void* scratch, size_t bytes) {
+  if (!s || !scratch) return IDTO_ERR_INVALID_ARG;
+  if (multi(s)) {
+    use_subs(s);
+    const size_t share = bytes / s->nsub;
+    for (int i = 0; i < s->nsub; ++i)
+      IDTO_CUDA_CHECK(cudaMemsetAsync(static_cast<char*>(scratch) + share * i, 0, share, s->sub_streams[i]));
+    return IDTO_OK;
+  }
+  use_main(s);
+  IDTO_CUDA_CHECK(cudaMemsetAsync(scratch, 0, bytes, s->stream));
+  return IDTO_OK;
+}
+
 int idto_synchronize(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  use_main(s);
   return check_status(s);
 }
 
@@ -737,6 +963,7 @@ long idto_launch_count(idto_solver_t s) { return s ? g_launch_counter - s->launc
 
 int idto_profile_enable(idto_solver_t s, int enable) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  use_main(s);
   cudaStreamSynchronize(s->stream);
   for (auto& kv : s->prof)
     for (auto& e : kv.second) cudaEventDestroy(e.a), cudaEventDestroy(e.b);

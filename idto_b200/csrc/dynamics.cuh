@@ -201,7 +201,7 @@ template <int G>
 __device__ __forceinline__ void PositionPhase(const SModel& M, const PosSmem& P, const SolverConsts& sc,
                                               int k, const double* qb) {
   const bool body = k < M.nb;
-  const int nbp = M.nbp;
+  constexpr int nbp = G;  // SoA stride == group size (tables and slabs are padded to it)
   int parent = -1, level = -1;
   M3 R_PB = identity3(), R_PF = identity3();
   V3 p_PB = {0, 0, 0};
@@ -297,7 +297,7 @@ __device__ __forceinline__ void VelocityPhase(const SModel& M, const PosSmem& P,
                                               const SolverConsts& sc, int k, const double* vb, const double* ab,
                                               bool with_bias, double* tau_b) {
   const bool body = k < M.nb;
-  const int nbp = M.nbp;
+  constexpr int nbp = G;
   int jtype = 0, parent = -1, level = -1;
   V3 axis = {0, 0, 1};
   V3 w = {0, 0, 0}, v = {0, 0, 0}, al = {0, 0, 0}, ac = {0, 0, 0};

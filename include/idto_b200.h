@@ -17,6 +17,8 @@
 #ifndef IDTO_B200_H_
 #define IDTO_B200_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -136,6 +138,10 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* prob,
                        const idto_params* params, int batch, idto_solver_t* out);
 int idto_solver_destroy(idto_solver_t s);
 
+/* Number of internal sub-batch streams (1..16; default 4 when batch >= 32, else 1): the batch is cut
+ * into contiguous sub-batches whose kernels overlap (latency-bound KKT sweeps of one sub-batch with
+ * the throughput-bound ID-partials kernels of another).  Results do not depend on it. */
+int idto_solver_set_substreams(idto_solver_t s, int n);
 /* stream: a cudaStream_t passed as void* (0 = default stream). */
 int idto_solver_set_stream(idto_solver_t s, void* stream);
 
@@ -198,6 +204,13 @@ int idto_resolve_async(idto_solver_t s, int max_iterations,
                        double* q_out, double* v_out, double* tau_out,
                        int* iters_out, double* stats_out);
 int idto_synchronize(idto_solver_t s);
+/* Stream-ordering point without a host wait: everything enqueued so far (on the internal sub-batch
+ * streams too) is ordered before whatever the caller enqueues next on the solver's stream, e.g. a
+ * CUDA event record. */
+int idto_fence(idto_solver_t s);
+/* Benchmark hygiene: overwrite `bytes` of caller-provided device scratch (larger than L2) in the
+ * solver's stream order, so that the next re-solve starts with a cold L2. */
+int idto_flush_l2(idto_solver_t s, void* scratch, size_t bytes);
 
 /* Number of kernel launches issued by this solver since creation. */
 long idto_launch_count(idto_solver_t s);

@@ -1,0 +1,93 @@
+// C++ twin of python_bindings/test/trajectory_optimizer_test.py written against include/idto_b200.hpp:
+// same class names and call sequence as code using the reference's optimizer/*.h.
+//   usage: test_api <spinner.txt>      (baked table from BakedModel.save_txt)
+#include <cstdio>
+#include <cstdlib>
+
+#include "idto_b200.hpp"
+
+using namespace idto::optimizer;
+
+#define CHECK(c)                                                   \
+  do {                                                             \
+    if (!(c)) {                                                    \
+      std::printf("CHECK failed: %s (line %d)\n", #c, __LINE__);   \
+      return 1;                                                    \
+    }                                                              \
+  } while (0)
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  const double time_step = 0.05;
+  MultibodyPlant plant = MultibodyPlant::LoadBaked(argv[1], time_step);
+  Diagram<double>* diagram = nullptr;
+
+  ProblemDefinition problem;
+  problem.num_steps = 40;
+  problem.q_init = VectorXd{0.3, 1.5, 0.0};
+  problem.v_init = VectorXd{0.0, 0.0, 0.0};
+  problem.Qq = 1.0 * MatrixXd::Identity(3, 3);
+  problem.Qv = 0.1 * MatrixXd::Identity(3, 3);
+  problem.R = MatrixXd::Diagonal({0.1, 0.1, 1e3});
+  problem.Qf_q = 10 * MatrixXd::Identity(3, 3);
+  problem.Qf_v = 0.1 * MatrixXd::Identity(3, 3);
+  for (int i = 0; i <= problem.num_steps; ++i) {
+    problem.q_nom.push_back(VectorXd{0.3, 1.5, 2.0});
+    problem.v_nom.push_back(VectorXd{0.0, 0.0, 0.0});
+  }
+  SolverParameters params;
+  params.max_iterations = 200;
+  params.scaling = true, params.equality_constraints = true;
+  params.Delta0 = 1e1, params.Delta_max = 1e5;
+  params.contact_stiffness = 200, params.dissipation_velocity = 0.1, params.smoothing_factor = 0.01;
+  params.friction_coefficient = 0.5, params.stiction_velocity = 0.05, params.verbose = false;
+  std::vector<VectorXd> q_guess(problem.num_steps + 1, VectorXd{0.3, 1.5, 0.0});
+
+  TrajectoryOptimizer<double> opt(diagram, &plant, problem, params);
+  CHECK(opt.time_step() == time_step && opt.num_steps() == 40);
+  CHECK(opt.unactuated_dofs().size() == 1 && opt.unactuated_dofs()[0] == 2);
+  CHECK(opt.num_equality_constraints() == 40);
+
+  TrajectoryOptimizerSolution<double> solution;
+  TrajectoryOptimizerStats<double> stats;
+  ConvergenceReason reason;
+  const SolverFlag flag = opt.Solve(q_guess, &solution, &stats, &reason);
+  CHECK(flag == SolverFlag::kMaxIterationsReached);
+  CHECK(solution.q.size() == 41 && solution.v.size() == 41 && solution.tau.size() == 40);
+  CHECK(stats.iteration_costs.size() == 200 && !stats.is_empty());
+  const double e0 = solution.q[40][0] - 0.287, e1 = solution.q[40][1] - 1.497, e2 = solution.q[40][2] - 1.995;
+  std::printf("q_T = %.5f %.5f %.5f  cost %.6f\n", solution.q[40][0], solution.q[40][1], solution.q[40][2],
+              stats.iteration_costs.back());
+  CHECK(std::sqrt(e0 * e0 + e1 * e1 + e2 * e2) < 1e-3);  // python_bindings/test/trajectory_optimizer_test.py:84-85
+
+  // warm start: 10 x SolveFromWarmStart(max_iterations = 1) appends stats, Delta persists (warm_start_test.py)
+  SolverParameters p1 = params;
+  p1.max_iterations = 1;
+  TrajectoryOptimizer<double> opt1(diagram, &plant, problem, p1);
+  auto ws = opt1.CreateWarmStart(q_guess);
+  TrajectoryOptimizerStats<double> st1;
+  for (int k = 0; k < 10; ++k) opt1.SolveFromWarmStart(ws.get(), &solution, &st1);
+  CHECK(st1.iteration_costs.size() == 10);
+  for (int k = 0; k < 10; ++k) CHECK(std::fabs(st1.iteration_costs[k] - stats.iteration_costs[k]) < 1e-8);
+  CHECK(ws->Delta() > 0 && ws->get_q().size() == 41);
+
+  // MPC mutators (h:463-483)
+  opt1.ResetInitialConditions(VectorXd{0.31, 1.49, 0.01}, VectorXd{0.0, 0.0, 0.0});
+  std::vector<VectorXd> qn = problem.q_nom;
+  qn[10] = VectorXd{0.4, 1.6, 2.1};
+  opt1.UpdateNominalTrajectory(qn, problem.v_nom);
+  CHECK(opt1.prob().q_nom[10][2] == 2.1 && opt1.prob().q_init[0] == 0.31);
+  opt1.SolveFromWarmStart(ws.get(), &solution, &st1);
+  CHECK(st1.iteration_costs.size() == 11);
+  CHECK(DecodeConvergenceReasons(kNoConvergenceCriteriaSatisfied) == "no convergence criterion satisfied");
+  bool threw = false;
+  try {
+    TrajectoryOptimizerStats<double> dirty = stats;
+    opt.Solve(q_guess, &solution, &dirty);
+  } catch (const std::runtime_error&) {
+    threw = true;  // stats must be empty (cc:2225)
+  }
+  CHECK(threw);
+  std::printf("C++ API test OK\n");
+  return 0;
+}

@@ -166,3 +166,74 @@ def test_warm_start_equals_one_shot_on_gpu(oracle_mod):
     qb, vb, _ = b.solution()
     assert np.max(np.abs(qa - qb)) < 1e-8 and np.max(np.abs(va - vb)) < 1e-8
     assert np.max(np.abs(sa[0] - sb)) < 1e-8
+
+
+def test_pyidto_mirror_spinner_like_reference_test(oracle_mod):
+    """python_bindings/test/trajectory_optimizer_test.py:17-106, same shape through idto_b200.pyidto."""
+    from idto_b200.pyidto import (BakedPlant, FindIdtoResource, ProblemDefinition, SolverParameters,
+                                  TrajectoryOptimizer, TrajectoryOptimizerSolution, TrajectoryOptimizerStats)
+    time_step = 0.05
+    plant = BakedPlant("spinner", time_step)
+    problem = ProblemDefinition()
+    problem.num_steps = 40
+    problem.q_init = np.array([0.3, 1.5, 0.0])
+    problem.v_init = np.array([0.0, 0.0, 0.0])
+    problem.Qq = 1.0 * np.eye(3)
+    problem.Qv = 0.1 * np.eye(3)
+    problem.R = np.diag([0.1, 0.1, 1e3])
+    problem.Qf_q = 10 * np.eye(3)
+    problem.Qf_v = 0.1 * np.eye(3)
+    problem.q_nom = [np.array([0.3, 1.5, 2.0]) for _ in range(41)]
+    problem.v_nom = [np.zeros(3) for _ in range(41)]
+    params = SolverParameters()
+    params.max_iterations = 200
+    params.Delta0, params.Delta_max = 1e1, 1e5
+    params.contact_stiffness, params.dissipation_velocity, params.smoothing_factor = 200, 0.1, 0.01
+    params.friction_coefficient, params.stiction_velocity, params.verbose = 0.5, 0.05, False
+    q_guess = [np.array([0.3, 1.5, 0.0]) for _ in range(41)]
+    opt = TrajectoryOptimizer(None, plant, problem, params)
+    assert opt.time_step() == time_step and opt.num_steps() == 40
+    solution, stats = TrajectoryOptimizerSolution(), TrajectoryOptimizerStats()
+    opt.Solve(q_guess, solution, stats)
+    assert len(solution.q) == 41 and len(solution.tau) == 40 and len(stats.iteration_costs) == 200
+    assert np.linalg.norm(solution.q[-1] - np.array([0.287, 1.497, 1.995])) < 1e-3
+    assert opt.prob().num_steps == 40 and opt.params().max_iterations == 200
+    new_q_nom = [x.copy() for x in problem.q_nom]
+    new_q_nom[10] = np.array([0.4, 1.6, 2.1])
+    opt.UpdateNominalTrajectory(new_q_nom, problem.v_nom)
+    assert np.all(opt.prob().q_nom[10] == np.array([0.4, 1.6, 2.1]))
+    with pytest.raises(RuntimeError):
+        FindIdtoResource("models/x.urdf")
+    # warm start: Delta persists, stats append (warm_start_test.py:104-112)
+    ws = opt.CreateWarmStart(q_guess)
+    params1 = opt.params()
+    st2 = TrajectoryOptimizerStats()
+    opt._params.max_iterations = 1
+    for _ in range(3):
+        opt.SolveFromWarmStart(ws, solution, st2)
+    assert len(st2.iteration_costs) == 3 and ws.Delta > 0 and len(ws.get_q()) == 41
+
+
+def test_substreams_do_not_change_results(oracle_mod):
+    """Sub-batch streams (default 4 when batch >= 32) only change scheduling: every batch element must be
+    bit-identical to the single-stream run, through both idto_solve and idto_resolve_async."""
+    from idto_b200 import capi
+    m, dt, prob, params, guess = problems.hopper(T=20, gradients_method=GRAD_CENTRAL)
+    B = 37
+    q0, v0, qg = problems.perturbed_batch(m, prob, B)
+    model = capi.Model(m)
+    out = {}
+    for ns in (1, 4):
+        gs = capi.BatchSolver(model, dt, prob, params, B)
+        gs.set_substreams(ns)
+        gs.reset_initial_conditions(q0, v0)
+        gs.set_q(qg)
+        it, _, stats = gs.solve(3)
+        for _ in range(2):  # asynchronous re-solves without host pointers
+            gs.invalidate()
+            gs.resolve_async(1)
+        gs.synchronize()
+        q, v, tau = gs.solution()
+        out[ns] = (it.copy(), stats.copy(), q.copy(), tau.copy(), gs.get("delta").copy())
+    for a, b in zip(out[1], out[4]):
+        assert np.array_equal(a, b)

@@ -21,10 +21,20 @@ gs = capi.BatchSolver(model, dt, prob, params, B)
 q0, v0, qg = problems.perturbed_batch(m, prob, B)
 gs.reset_initial_conditions(q0, v0)
 gs.set_q(qg)
-for _ in range(2):
+for _ in range(3):
     gs.invalidate()
     gs.resolve_async(1)
 gs.synchronize()
+for ns in (1, 2, 4, 8):
+    gs.set_substreams(ns)
+    gs.invalidate(); gs.resolve_async(1); gs.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        gs.invalidate()
+        gs.resolve_async(1)
+    gs.synchronize()
+    print(f"substreams={ns}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms/step (pipelined, wall)")
+gs.set_substreams(4)
 gs.profile_enable(True)
 t0 = time.perf_counter()
 for _ in range(steps):
@@ -56,7 +66,7 @@ try:
         b_ = time.perf_counter()
         gs.synchronize()
         c = time.perf_counter()
-        hq.copy_(oq)
+        hq.numpy()[...] = oq.numpy()
         d = time.perf_counter()
         if it >= 3:
             tt[0] += b_ - a; tt[1] += c - b_; tt[2] += d - c
