@@ -97,10 +97,11 @@ def cpu_arm(method, steps, warmup, nprob=BATCH, cores=None):
     m, dt, prob, params = workload(method)
     cores = cores or os.cpu_count() or 1
     nthreads = min(cores, nprob)
+    omp = max(1, cores // nprob)  # spare cores go to the reference's own OpenMP loops over t (cc:214, 455)
     q0, v0, qg = problems.perturbed_batch(m, prob, nprob)
     orcs = []
     for b in range(nprob):
-        o = oracle.Oracle(m, dt, prob, params, num_threads=1)
+        o = oracle.Oracle(m, dt, prob, params, num_threads=omp)
         o.reset_initial_conditions(q0[b], v0[b])
         o.set_q(qg[b])
         orcs.append(o)
@@ -117,7 +118,8 @@ def cpu_arm(method, steps, warmup, nprob=BATCH, cores=None):
         for _ in range(steps):
             iters += sum(ex.map(one, orcs))
         el = time.perf_counter() - t0
-    return iters / el, el / steps * 1e3, nthreads, f"{nprob} problems x {steps} iteration(s), {nthreads} host threads"
+    return (iters / el, el / steps * 1e3, nthreads * omp,
+            f"{nprob} problems x {steps} iteration(s), {nthreads} host threads x {omp} OpenMP threads each")
 
 
 def main():

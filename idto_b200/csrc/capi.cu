@@ -270,6 +270,10 @@ __global__ void k_set_delta(ProbCtl* ctl, const double* d, int B) {
 __global__ void k_fill(double* p, size_t n, double v) {
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = v;
 }
+// p[b*stride + i] = v for i < n, one CTA per b
+__global__ void k_fill_strided(double* p, size_t n, size_t stride, double v) {
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) p[blockIdx.x * stride + i] = v;
+}
 // Constant part of N+ (identity pattern for 1-dof / planar joints and floating translations).
 __global__ void k_init_nplus(DevModel dm, double* Np, int B, int T) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -568,7 +572,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   }
   // preset entries (inverse_dynamics_partials.h:35-42; state.h:68)
   const size_t blk = size_t(nv) * nq;
-  for (int b = 0; b < B; ++b) k_fill<<<1, 128>>>(bf.dqm + size_t(b) * T * blk, blk, std::numeric_limits<double>::quiet_NaN());
+  k_fill_strided<<<B, 128>>>(bf.dqm, blk, size_t(T) * blk, std::numeric_limits<double>::quiet_NaN());
   k_fill<<<64, 256>>>(bf.D, nvar, 1.0);
   k_init_nplus<<<(B * (T + 1) + 127) / 128, 128>>>(m->dm, bf.st.Nplus, B, T);
   k_init_nplus<<<(B * (T + 1) + 127) / 128, 128>>>(m->dm, bf.sc.Nplus, B, T);
