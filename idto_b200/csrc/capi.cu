@@ -340,7 +340,7 @@ void idto_params_default(idto_params* p) {  // optimizer/solver_parameters.h:64-
   p->contact_stiffness = 100, p->dissipation_velocity = 0.1, p->stiction_velocity = 0.05;
   p->friction_coefficient = 0.5, p->smoothing_factor = 0.1, p->scaling = 1;
   p->scaling_method = IDTO_SCALING_DOUBLE_SQRT, p->equality_constraints = 1;
-  p->Delta0 = 1e-1, p->Delta_max = 1e5, p->check_convergence = 0, p->linear_solver = IDTO_LINSOLVE_THOMAS;
+  p->Delta0 = 1e-1, p->Delta_max = 1e5, p->check_convergence = 0, p->linear_solver = IDTO_LINSOLVE_TWISTED;
 }
 
 int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
@@ -505,6 +505,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   sc.method = p->gradients_method, sc.scaling = p->scaling, sc.scaling_method = p->scaling_method;
   sc.eq = p->equality_constraints && sc.nh > 0, sc.normalize_quat = p->normalize_quaternions;
   sc.check_convergence = p->check_convergence;
+  sc.linear_solver = p->linear_solver;
   sc.k = p->contact_stiffness, sc.sigma = p->smoothing_factor, sc.vd = p->dissipation_velocity;
   sc.vs = p->stiction_velocity, sc.mu = p->friction_coefficient;
   const double eps = std::sqrt(std::numeric_limits<double>::epsilon());
@@ -731,6 +732,11 @@ long idto_field_size(idto_solver_t s, const char* field) {
   if (f == "g" || f == "D" || f == "gs" || f == "gm" || f == "dq" || f == "dqH") return c.n;
   if (f == "H_A" || f == "H_B" || f == "H_C" || f == "Hs_A" || f == "Hs_B" || f == "Hs_C") return (T + 1) * nq * nq;
   if (f == "J") return long(c.nh) * c.n;
+  {  // debugging views of the KKT sweep (block size kb = nq + nu when equality constraints are on)
+    const long kb = nq + (c.eq ? c.nu : 0);
+    if (f == "dbg_FY" || f == "dbg_FZ") return (T + 1) * kb * kb;
+    if (f == "dbg_Fr") return (T + 1) * kb;
+  }
   return IDTO_ERR_INVALID_ARG;
 }
 
@@ -768,6 +774,9 @@ int idto_get(idto_solver_t s, const char* field, double* out) {
   else if (f == "gm") src = bf.gm;
   else if (f == "dq") src = bf.dq;
   else if (f == "dqH") src = bf.dqH;
+  else if (f == "dbg_FY") src = bf.FY;
+  else if (f == "dbg_FZ") src = bf.FZ;
+  else if (f == "dbg_Fr") src = bf.X;
   if (src) {
     IDTO_CUDA_CHECK(cudaMemcpy(out, src, size_t(sz) * c.B * sizeof(double), cudaMemcpyDeviceToHost));
     return IDTO_OK;

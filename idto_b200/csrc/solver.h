@@ -40,7 +40,7 @@ struct DevModel {
 struct SolverConsts {
   int B, T, nq, nv, nu, n, nh;
   double dt;
-  int method, scaling, scaling_method, eq, normalize_quat, check_convergence;
+  int method, scaling, scaling_method, eq, normalize_quat, check_convergence, linear_solver;
   double k, sigma, vd, vs, mu, threshold;  // contact (cc:257-269)
   double Delta_max;
   double tol[6];

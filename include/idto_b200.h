@@ -89,7 +89,8 @@ typedef struct {
 enum { IDTO_GRAD_FORWARD = 0, IDTO_GRAD_CENTRAL = 1, IDTO_GRAD_CENTRAL4 = 2 };
 enum { IDTO_SCALING_SQRT = 0, IDTO_SCALING_ADAPTIVE_SQRT = 1,
        IDTO_SCALING_DOUBLE_SQRT = 2, IDTO_SCALING_ADAPTIVE_DOUBLE_SQRT = 3 };
-enum { IDTO_LINSOLVE_THOMAS = 0, IDTO_LINSOLVE_CYCLIC_REDUCTION = 1 };
+/* single top-down block-Thomas sweep, or two-sided ("twisted") elimination by a 2-CTA cluster */
+enum { IDTO_LINSOLVE_THOMAS = 0, IDTO_LINSOLVE_TWISTED = 1 };
 
 typedef struct {
   int max_iterations;         /* 100 */
@@ -109,7 +110,7 @@ typedef struct {
   double tol_rel_cost_reduction, tol_abs_cost_reduction;
   double tol_rel_gradient_along_dq, tol_abs_gradient_along_dq;
   double tol_rel_state_change, tol_abs_state_change;
-  int linear_solver;          /* IDTO_LINSOLVE_THOMAS (build-specific; reference: kPentaDiagonalLu) */
+  int linear_solver;          /* IDTO_LINSOLVE_TWISTED (build-specific; reference: kPentaDiagonalLu) */
 } idto_params;
 
 /* Fills `p` with the reference defaults (solver_parameters.h:64-167). */
