@@ -16,6 +16,13 @@
 namespace idto {
 
 long g_launch_counter = 0;
+bool use_chain_kernels(const DevModel& dm) {
+  static const bool force_group = [] {
+    const char* e = std::getenv("IDTO_DYNAMICS");
+    return e && std::string(e) == "group";
+  }();
+  return !force_group && chain_supported(dm);
+}
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
@@ -423,6 +430,58 @@ int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
   dm.o_gtype = push_i(d->geom_type, ng, ngp);
   dm.o_pA = push_i(d->pair_geomA, np, npp);
   dm.o_pB = push_i(d->pair_geomB, np, npp);
+  // ---- chain decomposition: a body's first child continues its chain, the others start new chains ----
+  {
+    std::vector<int> bchain(nb, -1), chain_top;
+    int nchains = 0;
+    for (int k = 0; k < nb; ++k) {  // bodies are in depth-first order: parents first
+      const int p = d->parent[k];
+      const bool continues = p >= 0 && child[size_t(0) * nbp + p] == k;  // first child of its parent
+      if (continues) {
+        bchain[k] = bchain[p];
+      } else {
+        bchain[k] = nchains++;
+        chain_top.push_back(k);
+      }
+    }
+    int CG = 1;
+    while (CG < nchains) CG *= 2;
+    dm.cgroup = CG, dm.nchains = nchains;
+    std::vector<int> levbody(size_t(kMaxLevels) * CG, -1), levcross(kMaxLevels, 0), plane(nb, -1);
+    if (nlevels > kMaxLevels || CG > 32) {
+      delete m;
+      set_last_error("tree too deep / too many chains for the chain-lane kernels");
+      return IDTO_ERR_UNSUPPORTED;
+    }
+    for (int k = 0; k < nb; ++k) {
+      levbody[size_t(level[k]) * CG + bchain[k]] = k;
+      const int p = d->parent[k];
+      if (p >= 0) {
+        plane[k] = bchain[p];
+        if (bchain[p] != bchain[k]) levcross[level[k]] = 1;
+      }
+    }
+    std::vector<int> gslot(nb, -1), gdyn(ngp, -1);
+    int ngb = 0, ngd = 0;
+    for (int gi = 0; gi < ng; ++gi) {
+      const int bdy = d->geom_body[gi];
+      if (bdy >= 0) {
+        gdyn[gi] = ngd++;
+        if (gslot[bdy] < 0) gslot[bdy] = ngb++;
+      }
+    }
+    dm.ngb = ngb, dm.ngd = ngd;
+    dm.chain_ok = (CG <= 8 && nlevels <= kMaxLevels) ? 1 : 0;
+    for (int k = 0; k < nb; ++k)  // multi-dof joints must hang off the world (R_WF == R_PF in the backward pass)
+      if ((d->joint_type[k] == IDTO_JOINT_PLANAR || d->joint_type[k] == IDTO_JOINT_QUAT_FLOATING) && d->parent[k] >= 0)
+        dm.chain_ok = 0;
+    dm.o_levbody = push_i(levbody.data(), kMaxLevels * CG, kMaxLevels * CG);
+    dm.o_levcross = push_i(levcross.data(), kMaxLevels, kMaxLevels);
+    dm.o_plane = push_i(plane.data(), nb, nbp);
+    dm.o_gslot = push_i(gslot.data(), nb, nbp);
+    dm.o_gdyn = push_i(gdyn.data(), ngp, ngp);
+    dm.o_bchain = push_i(bchain.data(), nb, nbp);
+  }
   while (it.size() % 4) it.push_back(0);
   // double table (SoA: field-major, body-minor)
   std::vector<double> dt;
@@ -441,6 +500,7 @@ int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
   dm.o_damping = push_soa(d->damping, 1, d->nv, d->nv);
   dm.o_gdims = push_soa(d->geom_dims, 3, ng, ngp);
   dm.o_XBG = push_soa(d->X_BG, 12, ng, ngp);
+  dm.o_XWGs = push_soa(d->X_BG, 12, ng, ngp);  // world-anchored geometries: X_WG == X_BG (body = world)
   while (dt.size() % 2) dt.push_back(0.0);
   dm.itab_bytes = int(it.size() * sizeof(int));
   dm.dtab_bytes = int(dt.size() * sizeof(double));

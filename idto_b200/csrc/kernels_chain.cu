@@ -1,0 +1,287 @@
+// Chain-lane versions of the inverse-dynamics kernels (tau and the ID partials); see dynamics_chain.cuh
+// for the decomposition and kernels_partials.cu for the finite-difference scheme they share:
+//   A  tau[t-1] at q_t +- dq e_i: full evaluations (pose computed on the fly, nothing but the contact
+//      geometry is kept per evaluation);
+//   B  tau[t] at the unperturbed q_{t+1}: body poses + contact geometry computed once per (b,t) slot and
+//      shared by the nq groups of the slot;
+//   C  dtau_{t+1}/dq_t = M(q_{t+2}) N+_{t+1} / dt^2 (cc:552-561): one bias-free evaluation on the shared pose.
+#include "dynamics_chain.cuh"
+
+namespace idto {
+
+namespace {
+
+struct ChainLayout {
+  int slots, groups, threads, smem_bytes;
+};
+
+// shared memory: tables | per slot 2 shared poses | per group: eval scratch + private pose + 3 tau rows
+__host__ __device__ inline int cgroup_doubles(const DevModel& dm, int nv) {
+  return ceval_doubles(dm) + cpose_private_doubles(dm) + 3 * nv;  // tau rows: +dq, -dq, and (+dq) - (-dq) for CD4
+}
+
+ChainLayout chain_layout(const DevModel& dm, int nq, int nv) {
+  ChainLayout L;
+  const int per_slot = nq * dm.cgroup;
+  const int budget = 216 * 1024 - model_smem_bytes(dm) - 8 * nv;
+  int best = 1;
+  for (int s = 1; s <= 64; ++s) {
+    const int threads = (s * per_slot + 31) / 32 * 32;
+    const int bytes = 8 * ((s + 1) * 2 * cpose_doubles(dm) + (threads / dm.cgroup) * cgroup_doubles(dm, nv));
+    if (threads <= 320 && bytes <= budget) best = s;
+  }
+  L.slots = best;
+  L.threads = (best * per_slot + 31) / 32 * 32;
+  L.groups = L.threads / dm.cgroup;
+  L.smem_bytes = model_smem_bytes(dm) + 8 * nv +
+                 8 * ((best + 1) * 2 * cpose_doubles(dm) + L.groups * cgroup_doubles(dm, nv));
+  return L;
+}
+
+}  // namespace
+
+template <int CG, int NLEV, int METHOD>
+__global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverConsts sc, SolverBufs bf, int slots,
+                                                           int force) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int T = sc.T, nq = sc.nq, nv = sc.nv;
+  const int g = threadIdx.x / CG, c = threadIdx.x % CG;
+  const int slot = g / nq, i = g % nq;
+  const int sg = blockIdx.x * slots + slot;
+  const bool valid = (slot < slots) && (sg < sc.B * T);
+  const int b = valid ? sg / T : 0;
+  const int t = valid ? sg % T + 1 : 1;
+  const bool live = valid && (force || bf.ctl[b].derivs_dirty);
+  if (!__syncthreads_or(live ? 1 : 0)) return;
+
+  int* si = reinterpret_cast<int*>(smem);
+  double* sd = reinterpret_cast<double*>(smem + dm.itab_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + dm.itab_bytes + dm.dtab_bytes);
+  double* base = reinterpret_cast<double*>(smem + model_smem_bytes(dm));
+  stage_model(dm, si, sd, bar);
+  const CModel C = make_cmodel(dm, si, sd);
+  double* zrow = base;  // nv zeros
+  for (int e = threadIdx.x; e < nv; e += blockDim.x) zrow[e] = 0.0;
+  base += nv;
+  const int pd = cpose_doubles(dm), gd = cgroup_doubles(dm, nv);
+  const int sslot = valid ? slot : slots;  // padding groups write their (discarded) poses to a dummy slot
+  const PoseSmem PB = make_cpose(dm, base + size_t(sslot) * 2 * pd);
+  const PoseSmem PC = make_cpose(dm, base + size_t(sslot) * 2 * pd + pd);
+  double* gbase = base + size_t(slots + 1) * 2 * pd + size_t(g) * gd;
+  const EvalSmem S = make_ceval(dm, gbase);
+  const PoseSmem PA = make_cpose_private(dm, gbase + ceval_doubles(dm));
+  double* T0 = gbase + ceval_doubles(dm) + cpose_private_doubles(dm);
+  double* T1 = T0 + nv;
+  double* T2 = T1 + nv;
+
+  const double* qB = bf.st.q + size_t(b) * (T + 1) * nq;
+  const double* vB = bf.st.v + size_t(b) * (T + 1) * nv;
+  const double* aB = bf.st.a + size_t(b) * T * nv;
+  const int tp1 = t < T ? t + 1 : t, tp2 = t < T - 1 ? t + 2 : t;  // clamped rows for predicated-off work
+
+  // ---- column bookkeeping (every lane computes it: no shuffles needed) ------------------------------------
+  const int owner = C.M.qowner[i];
+  const int ojt = C.M.jtype[owner], oq0 = C.M.qs[owner];
+  const int local = i - oq0;
+  const bool quatcol = ojt == IDTO_JOINT_QUAT_FLOATING && local < 4;
+  const int sl = (ojt == IDTO_JOINT_QUAT_FLOATING) ? local - 1 : local;
+  const double eps = 1.4901161193847656e-08;  // sqrt(2^-52)
+  const double qi = qB[size_t(t) * nq + i];
+  double dq = eps * fmax(1.0, fabs(qi));
+  {
+    const double temp = __dadd_rn(qi, dq);  // make dq representable (cc:506-508)
+    dq = __dadd_rn(temp, -qi);
+  }
+  const double dv = dq / sc.dt, da = dv / sc.dt;
+  V3 nt3 = {0, 0, 0}, ntp3 = {0, 0, 0};
+  if (quatcol) {
+    nt3 = quat_nplus_col(qB + size_t(t) * nq + oq0, local);
+    ntp3 = quat_nplus_col(qB + size_t(tp1) * nq + oq0, local);
+  }
+  Perturb pt;
+  pt.owner = owner, pt.local = local, pt.sl = sl, pt.quatcol = quatcol;
+  __syncthreads();  // zrow
+
+  // ---- phase 0: shared poses of q_{t+1} (even groups) and q_{t+2} (odd groups), first warp(s) of a slot ----
+  {
+    const bool mine = valid && i < 2 * CG && i < nq;  // enough groups to fill the warp that holds groups 0, 1
+    if (__any_sync(0xffffffffu, mine)) {
+      Perturb none = pt;
+      none.owner = -1;
+      if ((i & 1) == 0 || nq == 1)
+        chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PB, S, c, qB + size_t(tp1) * nq, vB, aB, none, T0);
+      else
+        chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PC, S, c, qB + size_t(tp2) * nq, vB, aB, none, T0);
+      if (nq == 1) chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PC, S, c, qB + size_t(tp2) * nq, vB, aB, none, T0);
+    }
+  }
+
+  constexpr int NK = METHOD == IDTO_GRAD_CENTRAL4 ? 4 : (METHOD == IDTO_GRAD_CENTRAL ? 2 : 1);
+  // combine the stencil points of one column: rows r = c, c+CG, ... of column i
+  auto emit = [&](double* __restrict__ dst_block, const double* __restrict__ tau_base, bool ok) {
+    __syncwarp();
+    if (ok && live)
+      for (int r = c; r < nv; r += CG) {
+        double val;
+        if (METHOD == IDTO_GRAD_FORWARD)
+          val = (T0[r] - tau_base[r]) / dq;  // cc:531, 539
+        else if (METHOD == IDTO_GRAD_CENTRAL)
+          val = 0.5 * (T0[r] - T1[r]) / dq;  // cc:785
+        else
+          val = 2.0 / 3.0 * T2[r] / dq - 1.0 / 12.0 * (T0[r] - T1[r]) / dq;  // cc:782-783 (T2 = tau+ - tau-)
+        dst_block[size_t(i) * nv + r] = val;
+      }
+    __syncwarp();
+  };
+  auto stash_d1 = [&]() {  // CD4: keep tau(+dq) - tau(-dq) while T0/T1 are reused for +-2dq
+    __syncwarp();
+    for (int r = c; r < nv; r += CG) T2[r] = T0[r] - T1[r];
+    __syncwarp();
+  };
+
+  // ---- A: tau[t-1] = ID(q_t^e, v_t^e, a_{t-1}^e)   (cc:526-531, 763-787) --------------------------------
+#pragma unroll 1
+  for (int kk = 0; kk < NK; ++kk) {
+    const double m = ((kk & 1) ? -1.0 : 1.0) * ((kk >= 2) ? 2.0 : 1.0);
+    pt.dq = m * dq, pt.cv = m * dv, pt.ca = m * da, pt.uv = 1.0, pt.ua = 1.0, pt.nv3 = nt3, pt.na3 = nt3;
+    chain_eval<CG, NLEV, kEvalFull>(C, sc, PA, S, c, qB + size_t(t) * nq, vB + size_t(t) * nv,
+                                    aB + size_t(t - 1) * nv, pt, (kk & 1) ? T1 : T0);
+    if (METHOD == IDTO_GRAD_CENTRAL4 && kk == 1) stash_d1();
+  }
+  emit(bf.dqp + (size_t(b) * T + (t - 1)) * nv * nq, bf.st.tau + (size_t(b) * T + (t - 1)) * nv, true);
+
+  __syncthreads();  // shared poses complete
+
+  // ---- B: tau[t] = ID(q_{t+1}, v_{t+1}^e, a_t^e)   (cc:533-540, 788-814) ---------------------------------
+  const int tb = t < T ? t : T - 1;  // a row index that exists even when the result is discarded
+#pragma unroll 1
+  for (int kk = 0; kk < NK; ++kk) {
+    const double m = ((kk & 1) ? -1.0 : 1.0) * ((kk >= 2) ? 2.0 : 1.0);
+    pt.dq = 0.0, pt.cv = -(m * dv), pt.ca = -(m * da), pt.uv = 1.0, pt.ua = 1.0 + 1.0;
+    pt.nv3 = ntp3, pt.na3 = ntp3 + nt3;
+    chain_eval<CG, NLEV, kEvalSharedPose>(C, sc, PB, S, c, qB + size_t(tp1) * nq, vB + size_t(tp1) * nv,
+                                          aB + size_t(tb) * nv, pt, (kk & 1) ? T1 : T0);
+    if (METHOD == IDTO_GRAD_CENTRAL4 && kk == 1) stash_d1();
+  }
+  emit(bf.dqt + (size_t(b) * T + tb) * nv * nq, bf.st.tau + (size_t(b) * T + tb) * nv, t < T);
+
+  // ---- C: dtau_dqm[t+1] = M(q_{t+2}) N+_{t+1} / dt^2   (cc:552-561) ---------------------------------------
+  pt.dq = 0.0, pt.cv = 0.0, pt.ca = 1.0, pt.uv = 1.0, pt.ua = 1.0, pt.nv3 = ntp3, pt.na3 = ntp3;
+  chain_eval<CG, NLEV, kEvalSharedPoseNoBias>(C, sc, PC, S, c, qB + size_t(tp2) * nq, zrow, zrow, pt, T0);
+  __syncwarp();
+  if (t < T - 1 && live) {
+    double* dst = bf.dqm + (size_t(b) * T + (t + 1)) * nv * nq + size_t(i) * nv;
+    for (int r = c; r < nv; r += CG) dst[r] = 1 / sc.dt / sc.dt * T0[r];
+  }
+}
+
+// tau_t = ID(q_{t+1}, v_{t+1}, a_t): one CG-lane group per (b, t).
+template <int CG, int NLEV>
+__global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc, TrajBuf tb,
+                                                   const ProbCtl* __restrict__ ctl, int force) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int* si = reinterpret_cast<int*>(smem);
+  double* sd = reinterpret_cast<double*>(smem + dm.itab_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + dm.itab_bytes + dm.dtab_bytes);
+  double* base = reinterpret_cast<double*>(smem + model_smem_bytes(dm));
+  stage_model(dm, si, sd, bar);
+  const CModel C = make_cmodel(dm, si, sd);
+  const int T = sc.T, nq = sc.nq, nv = sc.nv;
+  const int groups = blockDim.x / CG, grp = threadIdx.x / CG, c = threadIdx.x % CG;
+  const int gd = cgroup_doubles(dm, nv);
+  double* gbase = base + size_t(grp) * gd;
+  const EvalSmem S = make_ceval(dm, gbase);
+  const PoseSmem PA = make_cpose_private(dm, gbase + ceval_doubles(dm));
+  double* T0 = gbase + ceval_doubles(dm) + cpose_private_doubles(dm);
+  const int item = blockIdx.x * groups + grp;
+  const bool in_range = item < sc.B * T;
+  const int b = in_range ? item / T : 0, t = in_range ? item % T : 0;
+  const bool live = in_range && (force || ctl[b].traj_dirty);
+  Perturb none;
+  none.owner = -1, none.local = 0, none.sl = 0, none.quatcol = false;
+  none.dq = none.cv = none.ca = 0.0, none.uv = none.ua = 1.0, none.nv3 = none.na3 = {0, 0, 0};
+  chain_eval<CG, NLEV, kEvalFull>(C, sc, PA, S, c, tb.q + (size_t(b) * (T + 1) + t + 1) * nq,
+                                  tb.v + (size_t(b) * (T + 1) + t + 1) * nv, tb.a + (size_t(b) * T + t) * nv, none, T0);
+  __syncwarp();
+  if (live) {
+    double* tau = tb.tau + (size_t(b) * T + t) * nv;
+    for (int r = c; r < nv; r += CG) tau[r] = T0[r];
+  }
+}
+
+// ---- dispatch on (chain group size, padded tree depth) ------------------------------------------------------
+template <int CG, int NLEV>
+static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
+                                     cudaStream_t stream) {
+  const ChainLayout L = chain_layout(dm, sc.nq, sc.nv);
+  const int grid = (sc.B * sc.T + L.slots - 1) / L.slots;
+  g_launch_counter += 1;
+#define IDTO_LAUNCH_PC(METHOD)                                                                                   \
+  {                                                                                                              \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      cudaFuncSetAttribute(k_partials_chain<CG, NLEV, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                           224 * 1024);                                                                          \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    k_partials_chain<CG, NLEV, METHOD><<<grid, L.threads, L.smem_bytes, stream>>>(dm, sc, bf, L.slots, force);   \
+  }
+  switch (sc.method) {
+    case IDTO_GRAD_FORWARD: IDTO_LAUNCH_PC(IDTO_GRAD_FORWARD) break;
+    case IDTO_GRAD_CENTRAL: IDTO_LAUNCH_PC(IDTO_GRAD_CENTRAL) break;
+    default: IDTO_LAUNCH_PC(IDTO_GRAD_CENTRAL4) break;
+  }
+#undef IDTO_LAUNCH_PC
+}
+
+template <int CG, int NLEV>
+static void launch_tau_chain_cl(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl,
+                                bool force, cudaStream_t stream) {
+  const int threads = 128, groups = threads / CG;
+  const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv) * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_tau_chain<CG, NLEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    attr_set = true;
+  }
+  g_launch_counter += 1;
+  k_tau_chain<CG, NLEV><<<(sc.B * sc.T + groups - 1) / groups, threads, smem, stream>>>(dm, sc, tb, ctl, force);
+}
+
+// Instantiated (lanes per evaluation, padded tree depth) pairs; anything else falls back to the
+// one-lane-per-body kernels (chain_supported() is false).
+static int chain_key(const DevModel& dm) {
+  const int nl = dm.nlevels <= 2 ? 2 : (dm.nlevels <= 4 ? 4 : 8);
+  return dm.cgroup * 16 + nl;
+}
+#define IDTO_CHAIN_DISPATCH(FN, ...)              \
+  switch (chain_key(dm)) {                        \
+    case 1 * 16 + 2: FN<1, 2>(__VA_ARGS__); break; \
+    case 1 * 16 + 4: FN<1, 4>(__VA_ARGS__); break; \
+    case 1 * 16 + 8: FN<1, 8>(__VA_ARGS__); break; \
+    case 2 * 16 + 2: FN<2, 2>(__VA_ARGS__); break; \
+    case 2 * 16 + 4: FN<2, 4>(__VA_ARGS__); break; \
+    case 4 * 16 + 4: FN<4, 4>(__VA_ARGS__); break; \
+    case 8 * 16 + 4: FN<8, 4>(__VA_ARGS__); break; \
+    default: break;                               \
+  }
+
+bool chain_supported(const DevModel& dm) {
+  if (!dm.chain_ok) return false;
+  switch (chain_key(dm)) {
+    case 1 * 16 + 2: case 1 * 16 + 4: case 1 * 16 + 8: case 2 * 16 + 2: case 2 * 16 + 4: case 4 * 16 + 4:
+    case 8 * 16 + 4: return true;
+    default: return false;
+  }
+}
+
+void launch_partials_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
+                           cudaStream_t stream) {
+  IDTO_CHAIN_DISPATCH(launch_partials_chain_cl, dm, sc, bf, force, stream)
+}
+void launch_tau_chain(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl, bool force,
+                      cudaStream_t stream) {
+  IDTO_CHAIN_DISPATCH(launch_tau_chain_cl, dm, sc, tb, ctl, force, stream)
+}
+
+}  // namespace idto

@@ -268,6 +268,10 @@ static void launch_partials_g(const DevModel& dm, const SolverConsts& sc, const 
 
 void launch_partials(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
                      cudaStream_t stream) {
+  if (use_chain_kernels(dm)) {
+    launch_partials_chain(dm, sc, bf, force, stream);
+    return;
+  }
   switch (dm.group) {
     case 2: launch_partials_g<2>(dm, sc, bf, force, stream); break;
     case 4: launch_partials_g<4>(dm, sc, bf, force, stream); break;

@@ -166,6 +166,12 @@ void launch_traj(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b
 void launch_tau(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch, bool force,
                 cudaStream_t stream) {
   const TrajBuf& tb = scratch ? bf.sc : bf.st;
+  if (use_chain_kernels(dm)) {
+    launch_tau_chain(dm, sc, tb, bf.ctl, force, stream);
+    g_launch_counter += 1;
+    k_cost<<<sc.B, 64, 0, stream>>>(sc, tb, bf.q_nom, bf.v_nom, bf.ctl, force ? 1 : 0, scratch ? 0 : 1);
+    return;
+  }
   switch (dm.group) {
     case 2: launch_tau_g<2>(dm, sc, tb, bf.ctl, force, stream); break;
     case 4: launch_tau_g<4>(dm, sc, tb, bf.ctl, force, stream); break;

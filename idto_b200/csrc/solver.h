@@ -21,7 +21,8 @@
 namespace idto {
 
 constexpr int kMaxChildren = 8;
-constexpr int kMaxGroup = 32;  // bodies per inverse-dynamics evaluation group (lanes)
+constexpr int kMaxGroup = 32;
+constexpr int kMaxLevels = 8;    // tree depth supported by the chain-lane kernels  // bodies per inverse-dynamics evaluation group (lanes)
 
 // Baked model on the device: two SoA tables (ints, doubles) copied to shared memory by TMA.
 struct DevModel {
@@ -29,11 +30,16 @@ struct DevModel {
   const double* dtab;
   int itab_bytes, dtab_bytes;  // multiples of 16
   int nb, nbp, nq, nv, ng, np, npp, nlevels, group;  // nbp/npp: padded strides; group: lanes per evaluation
+  // chain decomposition (lane = kinematic chain, step = tree level): cgroup lanes per evaluation
+  int cgroup, nchains, ngb, ngd;  // ngb: bodies carrying geometry, ngd: geometries on moving bodies
+  int chain_ok;                   // the chain-lane kernels support this model
   double gx, gy, gz;
   // int table offsets (in ints)
   int o_parent, o_jtype, o_qs, o_vs, o_level, o_nchild, o_child, o_flags, o_qowner, o_gbody, o_gtype, o_pA, o_pB;
+  int o_levbody, o_levcross, o_plane, o_gslot, o_gdyn, o_bchain;  // chain tables
   // double table offsets (in doubles)
   int o_XPF, o_RMB, o_axis, o_mass, o_com, o_inertia, o_damping, o_gdims, o_XBG;
+  int o_XWGs;  // world pose of world-anchored geometries [12][ng]
 };
 
 // Constants of one TrajectoryOptimizer (problem + params), uniform across the batch.
@@ -103,6 +109,12 @@ void launch_dogleg(const SolverConsts& sc, const SolverBufs& b, cudaStream_t str
 void launch_trust_update(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool commit,
                          cudaStream_t stream);
 int partials_smem_bytes(const DevModel& dm, int nq);
+bool chain_supported(const DevModel& dm);
+void launch_partials_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
+                           cudaStream_t stream);
+void launch_tau_chain(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl, bool force,
+                      cudaStream_t stream);
+bool use_chain_kernels(const DevModel& dm);  // chain-lane kernels unless IDTO_DYNAMICS=group or unsupported
 extern long g_launch_counter;  // kernels launched by this library (all solvers)
 
 }  // namespace idto
