@@ -447,6 +447,8 @@ int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
     int CG = 1;
     while (CG < nchains) CG *= 2;
     dm.cgroup = CG, dm.nchains = nchains;
+    dm.cg_res = 4;  // measured best on B200 (residues 4 and 12 spread the stride-3 leg bodies over all banks)
+    if (const char* e = std::getenv("IDTO_CHAIN_RES")) dm.cg_res = std::atoi(e) & 15;
     std::vector<int> levbody(size_t(kMaxLevels) * CG, -1), levcross(kMaxLevels, 0), plane(nb, -1);
     if (nlevels > kMaxLevels || CG > 32) {
       delete m;

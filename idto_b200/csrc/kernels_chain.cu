@@ -1,3 +1,5 @@
+#include <cstdlib>
+#include <algorithm>
 // Chain-lane versions of the inverse-dynamics kernels (tau and the ID partials); see dynamics_chain.cuh
 // for the decomposition and kernels_partials.cu for the finite-difference scheme they share:
 //   A  tau[t-1] at q_t +- dq e_i: full evaluations (pose computed on the fly, nothing but the contact
@@ -16,25 +18,33 @@ struct ChainLayout {
 };
 
 // shared memory: tables | per slot 2 shared poses | per group: eval scratch + private pose + 3 tau rows
-__host__ __device__ inline int cgroup_doubles(const DevModel& dm, int nv) {
-  return ceval_doubles(dm) + cpose_private_doubles(dm) + 3 * nv;  // tau rows: +dq, -dq, and (+dq) - (-dq) for CD4
+// tau rows: +dq, -dq, and (+dq) - (-dq) for the 4th-order stencil
+__host__ __device__ inline int cgroup_doubles(const DevModel& dm, int nv, int ntau) {
+  const int n = ceval_doubles(dm) + cpose_private_doubles(dm) + ntau * nv;
+  return n + ((dm.cg_res - n) & 15);  // groups of one warp must not start in the same bank
 }
 
-ChainLayout chain_layout(const DevModel& dm, int nq, int nv) {
+// Padding groups (thread count rounded up to a warp) share one dummy area, so shared memory is sized by
+// the groups that do real work: slots * nq + 1.
+ChainLayout chain_layout(const DevModel& dm, int nq, int nv, int ntau) {
   ChainLayout L;
   const int per_slot = nq * dm.cgroup;
-  const int budget = 216 * 1024 - model_smem_bytes(dm) - 8 * nv;
+  const int budget = 226 * 1024 - model_smem_bytes(dm) - 8 * nv;
+  static const int max_slots = [] {  // tuning knob; 3 slots measured fastest on the quadruped
+    const char* e = std::getenv("IDTO_CHAIN_SLOTS");
+    return e ? std::max(1, std::atoi(e)) : 64;
+  }();
   int best = 1;
   for (int s = 1; s <= 64; ++s) {
     const int threads = (s * per_slot + 31) / 32 * 32;
-    const int bytes = 8 * ((s + 1) * 2 * cpose_doubles(dm) + (threads / dm.cgroup) * cgroup_doubles(dm, nv));
-    if (threads <= 320 && bytes <= budget) best = s;
+    const int bytes = 8 * ((s + 1) * 2 * cpose_doubles(dm) + (s * nq + 1) * cgroup_doubles(dm, nv, ntau));
+    if (threads <= 320 && bytes <= budget && s <= max_slots) best = s;
   }
   L.slots = best;
   L.threads = (best * per_slot + 31) / 32 * 32;
-  L.groups = L.threads / dm.cgroup;
+  L.groups = best * nq + 1;
   L.smem_bytes = model_smem_bytes(dm) + 8 * nv +
-                 8 * ((best + 1) * 2 * cpose_doubles(dm) + L.groups * cgroup_doubles(dm, nv));
+                 8 * ((best + 1) * 2 * cpose_doubles(dm) + L.groups * cgroup_doubles(dm, nv, ntau));
   return L;
 }
 
@@ -63,16 +73,18 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   double* zrow = base;  // nv zeros
   for (int e = threadIdx.x; e < nv; e += blockDim.x) zrow[e] = 0.0;
   base += nv;
-  const int pd = cpose_doubles(dm), gd = cgroup_doubles(dm, nv);
+  constexpr int NTAU = METHOD == IDTO_GRAD_CENTRAL4 ? 3 : 2;
+  const int pd = cpose_doubles(dm), gd = cgroup_doubles(dm, nv, NTAU);
   const int sslot = valid ? slot : slots;  // padding groups write their (discarded) poses to a dummy slot
   const PoseSmem PB = make_cpose(dm, base + size_t(sslot) * 2 * pd);
   const PoseSmem PC = make_cpose(dm, base + size_t(sslot) * 2 * pd + pd);
-  double* gbase = base + size_t(slots + 1) * 2 * pd + size_t(g) * gd;
+  const int gidx = slot < slots ? g : slots * nq;  // padding groups share one dummy area
+  double* gbase = base + size_t(slots + 1) * 2 * pd + size_t(gidx) * gd;
   const EvalSmem S = make_ceval(dm, gbase);
   const PoseSmem PA = make_cpose_private(dm, gbase + ceval_doubles(dm));
   double* T0 = gbase + ceval_doubles(dm) + cpose_private_doubles(dm);
   double* T1 = T0 + nv;
-  double* T2 = T1 + nv;
+  double* T2 = NTAU > 2 ? T1 + nv : T1;
 
   const double* qB = bf.st.q + size_t(b) * (T + 1) * nq;
   const double* vB = bf.st.v + size_t(b) * (T + 1) * nv;
@@ -188,7 +200,7 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
   const CModel C = make_cmodel(dm, si, sd);
   const int T = sc.T, nq = sc.nq, nv = sc.nv;
   const int groups = blockDim.x / CG, grp = threadIdx.x / CG, c = threadIdx.x % CG;
-  const int gd = cgroup_doubles(dm, nv);
+  const int gd = cgroup_doubles(dm, nv, 1);
   double* gbase = base + size_t(grp) * gd;
   const EvalSmem S = make_ceval(dm, gbase);
   const PoseSmem PA = make_cpose_private(dm, gbase + ceval_doubles(dm));
@@ -213,7 +225,7 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
 template <int CG, int NLEV>
 static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
                                      cudaStream_t stream) {
-  const ChainLayout L = chain_layout(dm, sc.nq, sc.nv);
+  const ChainLayout L = chain_layout(dm, sc.nq, sc.nv, sc.method == IDTO_GRAD_CENTRAL4 ? 3 : 2);
   const int grid = (sc.B * sc.T + L.slots - 1) / L.slots;
   g_launch_counter += 1;
 #define IDTO_LAUNCH_PC(METHOD)                                                                                   \
@@ -221,7 +233,7 @@ static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc,
     static bool attr_set = false;                                                                                \
     if (!attr_set) {                                                                                             \
       cudaFuncSetAttribute(k_partials_chain<CG, NLEV, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                           224 * 1024);                                                                          \
+                           227 * 1024);                                                                          \
       attr_set = true;                                                                                           \
     }                                                                                                            \
     k_partials_chain<CG, NLEV, METHOD><<<grid, L.threads, L.smem_bytes, stream>>>(dm, sc, bf, L.slots, force);   \
@@ -238,7 +250,7 @@ template <int CG, int NLEV>
 static void launch_tau_chain_cl(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl,
                                 bool force, cudaStream_t stream) {
   const int threads = 128, groups = threads / CG;
-  const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv) * 8;
+  const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv, 1) * 8;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_tau_chain<CG, NLEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);

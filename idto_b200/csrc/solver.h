@@ -33,6 +33,7 @@ struct DevModel {
   // chain decomposition (lane = kinematic chain, step = tree level): cgroup lanes per evaluation
   int cgroup, nchains, ngb, ngd;  // ngb: bodies carrying geometry, ngd: geometries on moving bodies
   int chain_ok;                   // the chain-lane kernels support this model
+  int cg_res;                     // per-group smem stride is padded to cg_res (mod 16 doubles): bank spread
   double gx, gy, gz;
   // int table offsets (in ints)
   int o_parent, o_jtype, o_qs, o_vs, o_level, o_nchild, o_child, o_flags, o_qowner, o_gbody, o_gtype, o_pA, o_pB;
