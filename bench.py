@@ -272,7 +272,7 @@ def main():
             traffic = json.load(f).get(f"id_partials_{args.method}")
     except OSError:
         pass
-    roofline = {"kernel": "k_partials", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "k_partials_chain", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
                 "avg_launch_ms": stage_ms["id_partials"],
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
