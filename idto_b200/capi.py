@@ -15,7 +15,8 @@ from .bake import BakedModel, ModelDesc, model_desc
 from .types import NUM_STATS, Params, ProblemDefinition, ProblemDesc, SolverParameters
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libidto_b200.so")
+# IDTO_B200_LIB selects another build of the same library (e.g. a -DIDTO_KKT_TIMING debug build)
+LIB_PATH = os.environ.get("IDTO_B200_LIB") or os.path.join(_HERE, "lib", "libidto_b200.so")
 _D = ctypes.POINTER(ctypes.c_double)
 _I = ctypes.POINTER(ctypes.c_int)
 _LIB = None

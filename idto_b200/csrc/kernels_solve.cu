@@ -19,45 +19,28 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdio>
 
+#include "kkt_view.cuh"
 #include "reduce.cuh"
 #include "solver.h"
 
+// Phase timing of the twisted sweep (debug builds only: make EXTRA=-DIDTO_KKT_TIMING).
+#ifdef IDTO_KKT_TIMING
+#define KT_DECL long long kt_t = clock64(), kt_acc[12] = {0};
+#define KT(i) { const long long kt_n = clock64(); kt_acc[i] += kt_n - kt_t; kt_t = kt_n; }
+#define KT_PRINT(b, dir)                                                                                    \
+  if (threadIdx.x == 0 && (b) == 0)                                                                         \
+    printf("kkt dir %d: load %lld gemm2 %lld gemm1 %lld lu %lld backsub %lld store %lld csync %lld iface_asm " \
+           "%lld iface_gj %lld csync2 %lld final_backsub %lld\n", dir, kt_acc[0], kt_acc[1], kt_acc[2],      \
+           kt_acc[3], kt_acc[4], kt_acc[5], kt_acc[6], kt_acc[7], kt_acc[8], kt_acc[9], kt_acc[10]);
+#else
+#define KT_DECL
+#define KT(i)
+#define KT_PRINT(b, dir)
+#endif
+
 namespace idto {
-
-namespace {
-
-constexpr int kMaxOwnCols = 13;  // ceil((3*32+1)/8) columns of [G|Y|Z|r] per warp
-
-struct KktView {
-  const double *SA, *SB, *SC;  // scaled Hessian lower bands of problem b: [T+1][nq*nq] column-major
-  const double *Jm, *Jt, *Jp;  // scaled Jacobian bands of problem b: [T][nu*nq] row-major (u, c)
-  int nq, nu, T, eq;
-};
-
-// Entry (r, c) of the lower-band blocks of the time-major KKT matrix (see file header).
-__device__ __forceinline__ double kkt_C(const KktView& V, int i, int r, int c) {
-  const int nq = V.nq;
-  if (r < nq && c < nq) return V.SC[size_t(i) * nq * nq + c * nq + r];
-  if (r >= nq && c >= nq) return (i == 0 && r == c) ? 1.0 : 0.0;  // dummy lambda_{-1}
-  if (i == 0) return 0.0;
-  const int u = (r >= nq ? r : c) - nq, cc = (r >= nq ? c : r);
-  return V.Jp[(size_t(i - 1) * V.nu + u) * nq + cc];
-}
-__device__ __forceinline__ double kkt_B(const KktView& V, int i, int r, int c) {  // block (i, i-1), i >= 1
-  const int nq = V.nq;
-  if (c >= nq) return 0.0;
-  if (r < nq) return V.SB[size_t(i) * nq * nq + c * nq + r];
-  return V.Jt[(size_t(i - 1) * V.nu + (r - nq)) * nq + c];
-}
-__device__ __forceinline__ double kkt_A(const KktView& V, int i, int r, int c) {  // block (i, i-2), i >= 2
-  const int nq = V.nq;
-  if (c >= nq) return 0.0;
-  if (r < nq) return V.SA[size_t(i) * nq * nq + c * nq + r];
-  return V.Jm[(size_t(i - 1) * V.nu + (r - nq)) * nq + c];
-}
-
-}  // namespace
 
 // Thread mapping: 8 warps; lane = block row r, warp w owns the columns j = w, w+8, ... of every
 // matrix, so column-major shared-memory accesses are conflict-free and a Gauss-Jordan step needs a
@@ -300,15 +283,6 @@ static void launch_kkt_dispatch(int kb, const SolverConsts& sc, const SolverBufs
 // Blk(i, i+2) = A_{i+2}^T as its "back" blocks).  The two chains meet in a 2kb x 2kb interface system for
 // (x_m, x_{m+1}); then both CTAs back-substitute their halves concurrently.  This halves the sequential
 // chain of (T+1)*kb pivot steps that bounds the single-sweep kernel.
-// Generic block of the symmetric KKT matrix.
-__device__ __forceinline__ double kkt_blk(const KktView& V, int i, int j, int r, int c) {
-  if (j == i) return kkt_C(V, i, r, c);
-  if (j == i - 1) return kkt_B(V, i, r, c);
-  if (j == i - 2) return kkt_A(V, i, r, c);
-  if (j == i + 1) return kkt_B(V, i + 1, c, r);
-  return kkt_A(V, i + 2, c, r);  // j == i + 2
-}
-
 template <int KB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
     k_kkt_twisted(SolverConsts sc, SolverBufs bf, int force) {
@@ -354,6 +328,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
   for (int e = tid; e < 2 * kb; e += blockDim.x) rm1[e] = 0.0;
   if (tid == 0) s_fail = 0;
   __syncthreads();
+  KT_DECL
   // inner dimension of the products with the "back-2"/"back-1" blocks: the lower-band blocks A_i, B_i have
   // only nq non-zero columns; their transposes (reversed sweep) do not
   const int jn = dir == 0 ? nq : kb;
@@ -388,6 +363,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
         M[3 * kk + r] = r < nq ? -gs[i * nq + r] : (i >= 1 ? -h[(i - 1) * sc.nu + (r - nq)] : 0.0);
     }
     __syncthreads();
+    KT(0)
     if (row) {
 #pragma unroll
       for (int mm = 0; mm < NCK; ++mm) {
@@ -411,6 +387,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
       }
     }
     __syncthreads();
+    KT(1)
     if (row) {
 #pragma unroll
       for (int mm = 0; mm < NCK; ++mm) {
@@ -435,6 +412,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
       }
     }
     __syncthreads();
+    KT(2)
     // LU with partial pivoting (unit-diagonal U: the pivot row is normalised), applied to the
     // right-hand sides [Yrhs | E | r] as well; then a barrier-free, column-parallel back-substitution.
     // (Gauss-Jordan is not backward stable for the bottom-up chain, whose diagonal blocks reach
@@ -477,6 +455,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
       }
       __syncthreads();
     }
+    KT(3)
     // back-substitution with the unit upper-triangular U = M[:, 0:kb]: one thread per right-hand side
     if (tid < W - kb) {
       double* col = M + (kb + tid) * kb;
@@ -492,6 +471,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
       for (int rr = 0; rr < KB; ++rr) col[rr] = x[rr];
     }
     __syncthreads();
+    KT(4)
     if (row) {
 #pragma unroll
       for (int mm = 0; mm < NCK; ++mm) {
@@ -513,10 +493,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
       }
     }
     __syncthreads();
+    KT(5)
   }
   if (tid == 0 && s_fail) atomicExch(bf.status, IDTO_ERR_FACTORIZATION);
   __threadfence();
   cluster.sync();  // both chains (and their Y, Z, r in HBM) are complete
+  KT(6)
 
   // ---- interface system for u = (x_mid, x_mid+1), solved by CTA 0 ----------------------------------------
   //   (I - Z_m Z'_{m+2}) x_m + (Y_m - Z_m Y'_{m+2}) x_{m+1} = r_m - Z_m r'_{m+2}
@@ -568,6 +550,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
       Q[e] = val;
     }
     __syncthreads();
+    KT(7)
     // Gauss-Jordan with partial pivoting on the n2 x (n2+1) system; warp 0 searches (two rows per lane)
     for (int c = 0; c < n2; ++c) {
       if (tid < 32) {
@@ -609,8 +592,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
     }
     for (int e = tid; e < n2; e += blockDim.x) xint[e] = Q[n2 * n2 + e];
     __threadfence();
+    KT(8)
   }
   cluster.sync();  // the interface solution is visible to both CTAs
+  KT(9)
 
   // ---- back-substitution of each half, warp 0 of each CTA ------------------------------------------------
   //   top half:    x_i = r_i - Y_i x_{i+1} - Z_i x_{i+2},  i = mid-1 .. 0
@@ -647,6 +632,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
     }
     __syncthreads();
   }
+  KT(10)
+  KT_PRINT(b, dir)
 }
 
 template <int KB>
@@ -712,8 +699,9 @@ void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBuf
   const int kb = sc.nq + (sc.eq ? sc.nu : 0);
   g_launch_counter += 2;
   // two-sided elimination needs at least 4 block rows per half to pay off; 2*kb interface unknowns must fit n
-  if (sc.linear_solver != IDTO_LINSOLVE_THOMAS && sc.T + 1 >= 8)
-    launch_kkt_twisted_dispatch<1>(kb, sc, bf, force, stream);
+  if (sc.linear_solver != IDTO_LINSOLVE_THOMAS && sc.T + 1 >= 8) {
+    if (!launch_kkt_tw2(kb, sc, bf, force, stream)) launch_kkt_twisted_dispatch<1>(kb, sc, bf, force, stream);
+  }
   else
     launch_kkt_dispatch<1>(kb, sc, bf, force, stream);
   k_merit<<<sc.B, 256, 0, stream>>>(sc, bf, force ? 1 : 0);

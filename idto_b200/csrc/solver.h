@@ -104,6 +104,8 @@ void launch_assemble(const DevModel& dm, const SolverConsts& sc, const SolverBuf
 void launch_factor(const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
 void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
                      cudaStream_t stream);
+// register-resident two-sided KKT sweep (kernels_kkt2.cu); false if this block size is not instantiated
+bool launch_kkt_tw2(int kb, const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
 void launch_conv_check(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
 void launch_clear_dirty(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
 void launch_dogleg(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
