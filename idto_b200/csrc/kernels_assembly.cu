@@ -10,26 +10,37 @@ namespace idto {
 
 namespace {
 
-// sum_r Aw(r,i) * C(r,j) over nv rows, where Aw(r,i) = A(r,i) * (w_r * ws) was staged once (same
-// operation order as the reference's (A^T W) C products); column-major nv x nq in shared memory.
-__device__ __forceinline__ double wdot(const double* Aw, const double* C, int nv, int ld, int i, int j) {
-  double acc = 0.0;
-  const double* a = Aw + i * ld;
-  const double* c = C + j * ld;
-#pragma unroll 6
-  for (int r = 0; r < nv; ++r) acc += a[r] * c[r];
-  return acc;
-}
+constexpr int kAsmThreads = 160;
+constexpr int kTile = 4;  // every thread accumulates a kTile x kTile tile of one product
+
+// The eight nv x nq blocks a row needs (column-major, the layout they have in HBM) ...
+enum Blk { kP0 = 0, kT0, kM1, kP1, kT1, kP2, kN0, kN1, kNumBlk };
+// ... and the eight products X^T W Y over the nv rows.  The first five are symmetric (lower tiles only).
+//   C_t     = Qq' + N0'N0 + P0'P0 + T0'T0 + M1'M1 + N1'N1
+//   B_{t+1} = P1'T0 + T1'M1 - N1'N1          A_{t+2} = P2'M1
+struct Prod {
+  int left, right, sym;
+};
+__device__ __constant__ Prod kProds[8] = {{kN0, kN0, 1}, {kP0, kP0, 1}, {kT0, kT0, 1}, {kM1, kM1, 1},
+                                          {kN1, kN1, 1}, {kP1, kT0, 0}, {kT1, kM1, 0}, {kP2, kM1, 0}};
 
 }  // namespace
 
 // One CTA per (b, t), t = 0..T: g_t, C_t, B_{t+1}, A_{t+2} and the scale factors D_t.
-__global__ void __launch_bounds__(128) k_assemble(SolverConsts sc, SolverBufs bf, int force) {
+//
+// The blocks go global -> shared as 1-D bulk TMA copies (they are contiguous in HBM and keep their
+// layout); every thread then owns a 4x4 output tile of one product and walks the nv rows two at a
+// time with 16-byte shared-memory loads: 8 LDS.128 per 32 FMA instead of the 2 LDS.64 per FMA of a
+// thread-per-entry mapping (the first version was shared-memory-pipe bound at 163 us).  The row
+// weights 2 dt R / 2 dt Qv / 2 Qf_v are applied to the left operand in registers, in the reference's
+// operation order ((X^T W) Y, cc:1103-1165); the products land in shared memory and are summed in the
+// reference's order.
+__global__ void __launch_bounds__(kAsmThreads) k_assemble(SolverConsts sc, SolverBufs bf, int force) {
   extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) uint64_t bar;
   const int b = blockIdx.x / (sc.T + 1), t = blockIdx.x % (sc.T + 1);
   if (!force && !bf.ctl[b].derivs_dirty) return;
   const int T = sc.T, nq = sc.nq, nv = sc.nv, blk = nv * nq, tid = threadIdx.x, nt = blockDim.x;
-  const int ld = nv | 1, sblk = ld * nq;  // odd leading dimension in shared memory: conflict-free columns
   const double dt = sc.dt;
   const size_t pb = size_t(b) * T * blk;  // partial blocks of problem b
   double* g = bf.g + size_t(b) * sc.n + size_t(t) * nq;
@@ -54,100 +65,200 @@ __global__ void __launch_bounds__(128) k_assemble(SolverConsts sc, SolverBufs bf
     }
     return;
   }
-  // stage the blocks this row needs: P_{t-1}, Tt_t, M_{t+1}, P_t, Tt_{t+1}, P_{t+1}, N_t, N_{t+1}
-  double* sP0 = sm;             // dqp[t-1]
-  double* sT0 = sP0 + sblk;      // dqt[t]
-  double* sM1 = sT0 + sblk;      // dqm[t+1]
-  double* sP1 = sM1 + sblk;      // dqp[t]
-  double* sT1 = sP1 + sblk;      // dqt[t+1]
-  double* sP2 = sT1 + sblk;      // dqp[t+1]
-  double* sN0 = sP2 + sblk;      // N+_t / dt
-  double* sN1 = sN0 + sblk;      // N+_{t+1} / dt
-  double* wP0 = sN1 + sblk;      // weighted copies (left operands): R' P_{t-1}, R' Tt_t, R' M_{t+1}, ...
-  double* wT0 = wP0 + sblk;
-  double* wM1 = wT0 + sblk;
-  double* wP1 = wM1 + sblk;
-  double* wT1 = wP1 + sblk;
-  double* wP2 = wT1 + sblk;
-  double* wN0 = wP2 + sblk;      // Qv' N+_t/dt  (Qf_v' at t = T)
-  double* wN1 = wN0 + sblk;      // Qv' (or Qf_v') N+_{t+1}/dt
-  double* sC = wN1 + sblk;       // C_t staging (for the diagonal)
+  // ---- stage the blocks this row needs ----------------------------------------------------------
+  const int blkp = (blk + 1) & ~1;            // block stride in shared memory (16-byte aligned)
+  const int ntl = (nq + kTile - 1) / kTile;   // tiles per side
+  const int npad = ntl * kTile;               // padded side of a product
+  double* sblk = sm;                          // [kNumBlk][blkp]
+  double* part = sm + kNumBlk * blkp;         // [8][npad * npad] products, column-major
+  double* gpart = part + 8 * npad * npad;     // [6][nq] gradient terms
   const double* Np = bf.st.Nplus + size_t(b) * (T + 1) * blk;
-  for (int e = tid; e < blk; e += nt) {
-    const int se = (e / nv) * ld + e % nv;
-    sP0[se] = bf.dqp[pb + size_t(t - 1) * blk + e];
-    sN0[se] = Np[size_t(t) * blk + e] * (1 / dt);
-    if (t < T) {
-      sT0[se] = bf.dqt[pb + size_t(t) * blk + e];
-      sP1[se] = bf.dqp[pb + size_t(t) * blk + e];
-      sN1[se] = Np[size_t(t + 1) * blk + e] * (1 / dt);
+  const double* src[kNumBlk];
+  src[kP0] = bf.dqp + pb + size_t(t - 1) * blk;
+  src[kN0] = Np + size_t(t) * blk;
+  src[kT0] = t < T ? bf.dqt + pb + size_t(t) * blk : nullptr;
+  src[kP1] = t < T ? bf.dqp + pb + size_t(t) * blk : nullptr;
+  src[kN1] = t < T ? Np + size_t(t + 1) * blk : nullptr;
+  src[kM1] = t < T - 1 ? bf.dqm + pb + size_t(t + 1) * blk : nullptr;
+  src[kT1] = t < T - 1 ? bf.dqt + pb + size_t(t + 1) * blk : nullptr;
+  src[kP2] = t < T - 1 ? bf.dqp + pb + size_t(t + 1) * blk : nullptr;
+  const bool bulk = (blk & 1) == 0;  // cp.async.bulk moves multiples of 16 bytes between 16-byte aligned addresses
+  if (bulk) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      fence_barrier_init();
     }
-    if (t < T - 1) {
-      sM1[se] = bf.dqm[pb + size_t(t + 1) * blk + e];
-      sT1[se] = bf.dqt[pb + size_t(t + 1) * blk + e];
-      sP2[se] = bf.dqp[pb + size_t(t + 1) * blk + e];
+    __syncthreads();
+    if (tid == 0) {
+      int nblk = 0;
+#pragma unroll
+      for (int k = 0; k < kNumBlk; ++k) nblk += src[k] != nullptr;
+      mbar_arrive_expect_tx(&bar, uint32_t(nblk * blk * 8));
+#pragma unroll
+      for (int k = 0; k < kNumBlk; ++k)
+        if (src[k]) tma_bulk_g2s(sblk + k * blkp, src[k], uint32_t(blk * 8), &bar);
     }
+    mbar_wait(&bar, 0);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kNumBlk; ++k)
+      if (src[k])
+        for (int e = tid; e < blk; e += nt) sblk[k * blkp + e] = src[k][e];
+    __syncthreads();
   }
-  __syncthreads();
-  const double two_dt = 2 * dt;
+  const double two_dt = 2 * dt, inv_dt = 1 / dt;
   const double* Qvn = (t == T - 1) ? sc.Qfv : sc.Qv;  // weight of the v_{t+1} term (cc:1054-1061, 1132-1147)
   const double Qvn_s = (t == T - 1) ? 2.0 : two_dt;
-  for (int e0 = tid; e0 < blk; e0 += nt) {
-    const int r = e0 % nv, e = (e0 / nv) * ld + r;
-    const double wr = sc.R[r] * two_dt;
-    wP0[e] = sP0[e] * wr;
-    wN0[e] = sN0[e] * (t < T ? sc.Qv[r] * two_dt : sc.Qfv[r] * 2.0);
-    if (t < T) {
-      wT0[e] = sT0[e] * wr;
-      wP1[e] = sP1[e] * wr;
-      wN1[e] = sN1[e] * (Qvn[r] * Qvn_s);
+  // row weight of the left operand of product k, and the 1/dt that turns N+ into a velocity partial
+  auto weight = [&](int k, int r) {
+    if (k == 0) return t < T ? sc.Qv[r] * two_dt : sc.Qfv[r] * 2.0;
+    if (k == 4) return Qvn[r] * Qvn_s;
+    return sc.R[r] * two_dt;
+  };
+  auto live = [&](int k) {  // products that exist at this t
+    if (t == T) return k <= 1;
+    if (t == T - 1) return k != 3 && k != 6 && k != 7;
+    return true;
+  };
+
+  // ---- products: one 4x4 tile per thread-task -----------------------------------------------------
+  const int nsym = ntl * (ntl + 1) / 2, nfull = ntl * ntl;
+  const int ntask = 5 * nsym + 3 * nfull;
+  const bool even = (nv & 1) == 0;
+  for (int task = tid; task < ntask; task += nt) {
+    int k, ti, tj;
+    if (task < 5 * nsym) {
+      k = task / nsym;
+      int rem = task - k * nsym;  // lower-triangle tile index -> (ti >= tj)
+      ti = 0;
+      while (rem >= ti + 1) rem -= ti + 1, ++ti;
+      tj = rem;
+    } else {
+      const int rem0 = task - 5 * nsym;
+      k = 5 + rem0 / nfull;
+      const int rem = rem0 - (k - 5) * nfull;
+      ti = rem % ntl, tj = rem / ntl;
     }
-    if (t < T - 1) {
-      wM1[e] = sM1[e] * wr;
-      wT1[e] = sT1[e] * wr;
-      wP2[e] = sP2[e] * wr;
+    double* out = part + k * npad * npad;
+    if (!live(k)) continue;
+    const Prod pr = kProds[k];
+    const double* A = sblk + pr.left * blkp;
+    const double* C = sblk + pr.right * blkp;
+    const double sa = k == 0 || k == 4 ? inv_dt : 1.0;  // N+ / dt on both sides of the velocity products
+    int ia[kTile], jc[kTile];
+#pragma unroll
+    for (int u = 0; u < kTile; ++u) {
+      ia[u] = min(ti * kTile + u, nq - 1) * nv;  // clamped: the padding rows are computed and discarded
+      jc[u] = min(tj * kTile + u, nq - 1) * nv;
     }
+    double acc[kTile][kTile] = {};
+    if (even) {
+      for (int r = 0; r < nv; r += 2) {
+        const double w0 = weight(k, r), w1 = weight(k, r + 1);
+        double2 a[kTile], c[kTile];
+#pragma unroll
+        for (int u = 0; u < kTile; ++u) {
+          a[u] = *reinterpret_cast<const double2*>(A + ia[u] + r);
+          c[u] = *reinterpret_cast<const double2*>(C + jc[u] + r);
+        }
+#pragma unroll
+        for (int u = 0; u < kTile; ++u) {
+          const double a0 = (a[u].x * sa) * w0, a1 = (a[u].y * sa) * w1;
+#pragma unroll
+          for (int v = 0; v < kTile; ++v) {
+            acc[u][v] = fma(a0, c[v].x * sa, acc[u][v]);
+            acc[u][v] = fma(a1, c[v].y * sa, acc[u][v]);
+          }
+        }
+      }
+    } else {
+      for (int r = 0; r < nv; ++r) {
+        const double w0 = weight(k, r);
+#pragma unroll
+        for (int u = 0; u < kTile; ++u) {
+          const double a0 = (A[ia[u] + r] * sa) * w0;
+#pragma unroll
+          for (int v = 0; v < kTile; ++v) acc[u][v] = fma(a0, C[jc[v] + r] * sa, acc[u][v]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kTile; ++u)
+#pragma unroll
+      for (int v = 0; v < kTile; ++v) out[(tj * kTile + v) * npad + ti * kTile + u] = acc[u][v];
+  }
+  // ---- gradient terms (cc:1021-1081): six mat-vecs, one (term, column) per thread-task -----------
+  const double* q = bf.st.q + (size_t(b) * (T + 1) + t) * nq;
+  const double* qn = bf.q_nom + (size_t(b) * (T + 1) + t) * nq;
+  const double* v = bf.st.v + (size_t(b) * (T + 1) + t) * nv;
+  const double* vn = bf.v_nom + (size_t(b) * (T + 1) + t) * nv;
+  const double* tau = bf.st.tau + size_t(b) * T * nv;
+  for (int task = tid; task < 5 * nq; task += nt) {
+    const int term = task / nq, j = task - term * nq;
+    double x = 0.0;
+    if (term == 0) {  // (Qv' v~_t)^T dvt_dqt[t]
+      const double* N0 = sblk + kN0 * blkp + j * nv;
+      if (t < T)
+        for (int r = 0; r < nv; ++r) x += ((v[r] - vn[r]) * (sc.Qv[r] * two_dt)) * (N0[r] * inv_dt);
+      else
+        for (int r = 0; r < nv; ++r) x += ((v[r] - vn[r]) * (sc.Qfv[r] * 2)) * (N0[r] * inv_dt);
+    } else if (term == 1) {  // (Q' v~_{t+1})^T dvt_dqm[t+1]
+      const double* N1 = sblk + kN1 * blkp + j * nv;
+      if (t < T)
+        for (int r = 0; r < nv; ++r) x += ((v[nv + r] - vn[nv + r]) * (Qvn[r] * Qvn_s)) * (-(N1[r] * inv_dt));
+    } else if (term == 2) {  // (R' tau_{t-1})^T dtau_dqp[t-1]
+      const double* P0 = sblk + kP0 * blkp + j * nv;
+      for (int r = 0; r < nv; ++r) x += (tau[(t - 1) * nv + r] * (sc.R[r] * two_dt)) * P0[r];
+    } else if (term == 3) {  // (R' tau_t)^T dtau_dqt[t]
+      const double* T0 = sblk + kT0 * blkp + j * nv;
+      if (t < T)
+        for (int r = 0; r < nv; ++r) x += (tau[t * nv + r] * (sc.R[r] * two_dt)) * T0[r];
+    } else {  // (R' tau_{t+1})^T dtau_dqm[t+1]
+      const double* M1 = sblk + kM1 * blkp + j * nv;
+      if (t < T - 1)
+        for (int r = 0; r < nv; ++r) x += (tau[(t + 1) * nv + r] * (sc.R[r] * two_dt)) * M1[r];
+    }
+    gpart[term * nq + j] = x;
   }
   __syncthreads();
 
-  // ---- Hessian bands --------------------------------------------------------------------------
+  // ---- Hessian bands: sum the products in the reference's order; MakeSymmetric -------------------
+  auto P = [&](int k, int i, int j) { return part[k * npad * npad + j * npad + i]; };
+  auto Psym = [&](int k, int i, int j) { return i >= j ? P(k, i, j) : P(k, j, i); };
   for (int e = tid; e < nq * nq; e += nt) {
     const int j = e / nq, i = e % nq;  // column-major: entry (i, j)
+    const int il = i >= j ? i : j, jl = i >= j ? j : i;  // penta_diagonal_matrix.cc:74-76: upper of C := lower
     if (t < T) {
       double c = (i == j) ? sc.Qq[i] * two_dt : 0.0;
-      c += wdot(wN0, sN0, nv, ld, i, j);
-      c += wdot(wP0, sP0, nv, ld, i, j);
-      c += wdot(wT0, sT0, nv, ld, i, j);
-      if (t < T - 1) {
-        c += wdot(wM1, sM1, nv, ld, i, j);
-        c += wdot(wN1, sN1, nv, ld, i, j);
-      } else {
-        c += wdot(wN1, sN1, nv, ld, i, j);
-      }
-      sC[e] = c;
-      // B_{t+1}: dg_t/dq_{t+1}
-      double bb = wdot(wP1, sT0, nv, ld, i, j);
-      if (t < T - 1) bb += wdot(wT1, sM1, nv, ld, i, j);
-      bb += -wdot(wN1, sN1, nv, ld, i, j);  // dvt_dqt[t+1]^T Q dvt_dqm[t+1] = -(N/dt)^T Q (N/dt)
+      c += P(0, il, jl);
+      c += P(1, il, jl);
+      c += P(2, il, jl);
+      if (t < T - 1) c += P(3, il, jl);
+      c += P(4, il, jl);
+      HC[size_t(t) * nq * nq + e] = c;
+      double bb = P(5, i, j);
+      if (t < T - 1) bb += P(6, i, j);
+      bb += -Psym(4, i, j);  // dvt_dqt[t+1]^T Q dvt_dqm[t+1] = -(N/dt)^T Q (N/dt)
       HB[size_t(t + 1) * nq * nq + e] = bb;
-      if (t < T - 1) HA[size_t(t + 2) * nq * nq + e] = wdot(wP2, sM1, nv, ld, i, j);
+      if (t < T - 1) HA[size_t(t + 2) * nq * nq + e] = P(7, i, j);
     } else {  // cc:1157-1161
       double c = (i == j) ? sc.Qfq[i] * 2 : 0.0;
-      c += wdot(wN0, sN0, nv, ld, i, j);
-      c += wdot(wP0, sP0, nv, ld, i, j);
-      sC[e] = c;
+      c += P(0, il, jl);
+      c += P(1, il, jl);
+      HC[size_t(t) * nq * nq + e] = c;
     }
   }
-  __syncthreads();
-  // MakeSymmetric (penta_diagonal_matrix.cc:74-76): strictly-upper of C := lower
-  for (int e = tid; e < nq * nq; e += nt) {
-    const int j = e / nq, i = e % nq;
-    HC[size_t(t) * nq * nq + e] = (i >= j) ? sC[e] : sC[i * nq + j];
-  }
-  // ---- scale factors (cc:1235-1254) ------------------------------------------------------------
-  if (sc.scaling) {
-    for (int e = tid; e < nq; e += nt) {
-      const double hd = sC[e * nq + e];
+  // ---- scale factors (cc:1235-1254) and gradient ----------------------------------------------------
+  for (int e = tid; e < nq; e += nt) {
+    if (sc.scaling) {
+      double hd = t < T ? sc.Qq[e] * two_dt : sc.Qfq[e] * 2;
+      hd += P(0, e, e);
+      hd += P(1, e, e);
+      if (t < T) {
+        hd += P(2, e, e);
+        if (t < T - 1) hd += P(3, e, e);
+        hd += P(4, e, e);
+      }
       switch (sc.scaling_method) {
         case IDTO_SCALING_SQRT: D[e] = fmin(1.0, 1 / sqrt(hd)); break;
         case IDTO_SCALING_ADAPTIVE_SQRT: D[e] = fmin(D[e], 1 / sqrt(hd)); break;
@@ -155,44 +266,20 @@ __global__ void __launch_bounds__(128) k_assemble(SolverConsts sc, SolverBufs bf
         default: D[e] = fmin(D[e], 1 / sqrt(sqrt(hd))); break;
       }
     }
-  }
-  // ---- gradient ---------------------------------------------------------------------------------
-  const double* q = bf.st.q + (size_t(b) * (T + 1) + t) * nq;
-  const double* qn = bf.q_nom + (size_t(b) * (T + 1) + t) * nq;
-  const double* v = bf.st.v + (size_t(b) * (T + 1) + t) * nv;
-  const double* vn = bf.v_nom + (size_t(b) * (T + 1) + t) * nv;
-  const double* tau = bf.st.tau + size_t(b) * T * nv;
-  for (int j = tid; j < nq; j += nt) {
     double gj;
     if (t < T) {
-      gj = (q[j] - qn[j]) * (sc.Qq[j] * two_dt);
-      double x = 0.0;
-      for (int r = 0; r < nv; ++r) x += ((v[r] - vn[r]) * (sc.Qv[r] * two_dt)) * sN0[j * ld + r];
-      gj += x;
-      x = 0.0;
-      for (int r = 0; r < nv; ++r) x += ((v[nv + r] - vn[nv + r]) * (Qvn[r] * Qvn_s)) * (-sN1[j * ld + r]);
-      gj += x;
-      x = 0.0;
-      for (int r = 0; r < nv; ++r) x += (tau[(t - 1) * nv + r] * (sc.R[r] * two_dt)) * sP0[j * ld + r];
-      gj += x;
-      x = 0.0;
-      for (int r = 0; r < nv; ++r) x += (tau[t * nv + r] * (sc.R[r] * two_dt)) * sT0[j * ld + r];
-      gj += x;
-      if (t != T - 1) {
-        x = 0.0;
-        for (int r = 0; r < nv; ++r) x += (tau[(t + 1) * nv + r] * (sc.R[r] * two_dt)) * sM1[j * ld + r];
-        gj += x;
-      }
+      gj = (q[e] - qn[e]) * (sc.Qq[e] * two_dt);
+      gj += gpart[0 * nq + e];
+      gj += gpart[1 * nq + e];
+      gj += gpart[2 * nq + e];
+      gj += gpart[3 * nq + e];
+      if (t != T - 1) gj += gpart[4 * nq + e];
     } else {  // cc:1074-1080
-      double x = 0.0;
-      for (int r = 0; r < nv; ++r) x += (tau[(T - 1) * nv + r] * (sc.R[r] * two_dt)) * sP0[j * ld + r];
-      gj = x;
-      gj += (q[j] - qn[j]) * (sc.Qfq[j] * 2);
-      x = 0.0;
-      for (int r = 0; r < nv; ++r) x += ((v[r] - vn[r]) * (sc.Qfv[r] * 2)) * sN0[j * ld + r];
-      gj += x;
+      gj = gpart[2 * nq + e];
+      gj += (q[e] - qn[e]) * (sc.Qfq[e] * 2);
+      gj += gpart[0 * nq + e];
     }
-    g[j] = gj;
+    g[e] = gj;
   }
 }
 
@@ -229,14 +316,15 @@ __global__ void __launch_bounds__(128) k_scale(SolverConsts sc, SolverBufs bf, i
 void launch_assemble(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
                      cudaStream_t stream) {
   (void)dm;
-  const int smem = (16 * (sc.nv | 1) * sc.nq + sc.nq * sc.nq) * 8;
+  const int blkp = (sc.nv * sc.nq + 1) & ~1, npad = (sc.nq + kTile - 1) / kTile * kTile;
+  const int smem = (kNumBlk * blkp + 8 * npad * npad + 6 * sc.nq) * 8;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   g_launch_counter += 2;
-  k_assemble<<<sc.B*(sc.T + 1), 128, smem, stream>>>(sc, bf, force ? 1 : 0);
+  k_assemble<<<sc.B*(sc.T + 1), kAsmThreads, smem, stream>>>(sc, bf, force ? 1 : 0);
   k_scale<<<sc.B*(sc.T + 1), 128, 0, stream>>>(sc, bf, force ? 1 : 0);
 }
 
