@@ -179,7 +179,7 @@ void make_view(const idto_solver_s* s, int b0, int nb, SolverConsts* scv, Solver
   for (double** p : {&v.HA, &v.HB, &v.HC, &v.SA, &v.SB, &v.SC}) *p += o * T1 * nq * nq;
   v.Jm += o * T * nuq, v.Jt += o * T * nuq, v.Jp += o * T * nuq;
   v.FY += o * T1 * kb * kb, v.FZ += o * T1 * kb * kb, v.X += o * T1 * kb, v.rhs += o * nh;
-  v.pH += o * n, v.dq += o * n, v.dqH += o * n, v.tmp1 += o * n, v.tmp2 += o * n, v.red += o * 8;
+  v.pH += o * n, v.dq += o * n, v.dqH += o * n, v.tmp1 += o * n, v.tmp2 += o * n, v.red += o * 8, v.part += o * T1 * 4, v.cnt += o;
   v.ctl += o;
   if (v.stats) v.stats += o * size_t(v.stats_cap) * IDTO_NUM_STATS;
   *bfv = v;
@@ -607,6 +607,8 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   alloc(&bf.rhs, size_t(B) * nh);
   alloc(&bf.pH, nvar), alloc(&bf.dq, nvar), alloc(&bf.dqH, nvar), alloc(&bf.tmp1, nvar), alloc(&bf.tmp2, nvar);
   alloc(&bf.red, size_t(B) * 8);
+  alloc(&bf.part, size_t(B) * (T + 1) * 4);
+  ok = ok && A.get(&bf.cnt, B) == cudaSuccess;
   ok = ok && A.get(&bf.ctl, B) == cudaSuccess && A.get(&bf.status, 1) == cudaSuccess;
   if (!ok) {
     set_last_error("cudaMalloc failed while creating the solver workspace");

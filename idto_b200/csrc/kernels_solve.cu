@@ -657,38 +657,6 @@ static void launch_kkt_twisted_dispatch(int kb, const SolverConsts& sc, const So
   }
 }
 
-// gm = g~ + J~^T lambda (cc:1442) and merit = L + h.lambda (cc:1418); one CTA per problem.
-__global__ void __launch_bounds__(256) k_merit(SolverConsts sc, SolverBufs bf, int force) {
-  __shared__ double red[32];
-  const int b = blockIdx.x;
-  if (!force && !bf.ctl[b].derivs_dirty) return;
-  const int n = sc.n, nh = sc.nh, nu = sc.nu, k = sc.nq, T = sc.T, tid = threadIdx.x, nt = blockDim.x;
-  const double* gs = bf.gs + size_t(b) * n;
-  double* gm = bf.gm + size_t(b) * n;
-  if (!sc.eq || nh == 0) {
-    for (int e = tid; e < n; e += nt) gm[e] = gs[e];
-    if (tid == 0) bf.merit[b] = bf.st.cost[b];
-    return;
-  }
-  const double* lam = bf.lambda + size_t(b) * nh;
-  for (int e = tid; e < n; e += nt) {
-    const int s = e / k, c = e % k;
-    double acc = 0.0;
-    if (s >= 1)  // rows (s-1, u): Jp[s-1]
-      for (int u = 0; u < nu; ++u) acc += bf.Jp[((size_t(b) * T + (s - 1)) * nu + u) * k + c] * lam[(s - 1) * nu + u];
-    if (s < T)  // rows (s, u): Jt[s]
-      for (int u = 0; u < nu; ++u) acc += bf.Jt[((size_t(b) * T + s) * nu + u) * k + c] * lam[s * nu + u];
-    if (s + 1 < T)  // rows (s+1, u): Jm[s+1]
-      for (int u = 0; u < nu; ++u) acc += bf.Jm[((size_t(b) * T + (s + 1)) * nu + u) * k + c] * lam[(s + 1) * nu + u];
-    gm[e] = gs[e] + acc;
-  }
-  double part = 0.0;
-  const double* h = bf.st.h + size_t(b) * nh;
-  for (int e = tid; e < nh; e += nt) part += h[e] * lam[e];
-  part = block_sum(part, red);
-  if (tid == 0) bf.merit[b] = bf.st.cost[b] + part;
-}
-
 void launch_factor(const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
   (void)sc, (void)bf, (void)force, (void)stream;  // fused into launch_lagrange (k_kkt_solve)
 }
@@ -697,14 +665,14 @@ void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBuf
                      cudaStream_t stream) {
   (void)dm;
   const int kb = sc.nq + (sc.eq ? sc.nu : 0);
-  g_launch_counter += 2;
+  g_launch_counter += 1;
   // two-sided elimination needs at least 4 block rows per half to pay off; 2*kb interface unknowns must fit n
   if (sc.linear_solver != IDTO_LINSOLVE_THOMAS && sc.T + 1 >= 8) {
     if (!launch_kkt_tw2(kb, sc, bf, force, stream)) launch_kkt_twisted_dispatch<1>(kb, sc, bf, force, stream);
   }
   else
     launch_kkt_dispatch<1>(kb, sc, bf, force, stream);
-  k_merit<<<sc.B, 256, 0, stream>>>(sc, bf, force ? 1 : 0);
+  launch_gm_matvec(sc, bf, force, stream);  // gm, merit, gHg, g.g
 }
 
 }  // namespace idto

@@ -8,53 +8,127 @@ namespace idto {
 
 namespace {
 
-// y = H~ x for the symmetric block penta-diagonal matrix given by its lower bands
+constexpr int kRowThreads = 128;
+
+// Block row i of y = H~ x for the symmetric block penta-diagonal matrix given by its lower bands
 // (PentaDiagonalMatrix::MultiplyBy, penta_diagonal_matrix.cc:181-207; D_i = B_{i+1}^T, E_i = A_{i+2}^T).
-__device__ __forceinline__ void penta_matvec(const SolverConsts& sc, const double* SA, const double* SB,
-                                             const double* SC, const double* x, double* y, int tid, int nt) {
+// xs[5][k] holds the blocks i-2..i+2 of x (zeros outside the matrix); thread-task (term, row) computes one
+// k-long dot product into terms[5][k]; the caller sums the five terms in the reference's order.
+__device__ __forceinline__ void block_row_matvec(const SolverConsts& sc, const double* SA, const double* SB,
+                                                 const double* SC, int i, const double* xs, double* terms, int tid,
+                                                 int nt) {
   const int k = sc.nq, kk = k * k, nblk = sc.T + 1;
-  for (int e = tid; e < sc.n; e += nt) {
-    const int i = e / k, r = e % k;
+  for (int task = tid; task < 5 * k; task += nt) {
+    const int term = task / k, r = task - term * k;
     double acc = 0.0;
-    const double* C = SC + size_t(i) * kk;
-    for (int c = 0; c < k; ++c) acc += C[c * k + r] * x[i * k + c];
-    if (i >= 1) {
-      const double* Bm = SB + size_t(i) * kk;
-      for (int c = 0; c < k; ++c) acc += Bm[c * k + r] * x[(i - 1) * k + c];
+    if (term == 0) {
+      const double* C = SC + size_t(i) * kk;
+      const double* x = xs + 2 * k;
+      for (int c = 0; c < k; ++c) acc += C[c * k + r] * x[c];
+    } else if (term == 1) {
+      if (i >= 1) {
+        const double* Bm = SB + size_t(i) * kk;
+        const double* x = xs + k;
+        for (int c = 0; c < k; ++c) acc += Bm[c * k + r] * x[c];
+      }
+    } else if (term == 2) {
+      if (i >= 2) {
+        const double* Am = SA + size_t(i) * kk;
+        for (int c = 0; c < k; ++c) acc += Am[c * k + r] * xs[c];
+      }
+    } else if (term == 3) {
+      if (i < nblk - 1) {
+        const double* Bn = SB + size_t(i + 1) * kk;  // D_i(r,c) = B_{i+1}(c,r)
+        const double* x = xs + 3 * k;
+        for (int c = 0; c < k; ++c) acc += Bn[r * k + c] * x[c];
+      }
+    } else {
+      if (i < nblk - 2) {
+        const double* An = SA + size_t(i + 2) * kk;
+        const double* x = xs + 4 * k;
+        for (int c = 0; c < k; ++c) acc += An[r * k + c] * x[c];
+      }
     }
-    if (i >= 2) {
-      const double* Am = SA + size_t(i) * kk;
-      for (int c = 0; c < k; ++c) acc += Am[c * k + r] * x[(i - 2) * k + c];
-    }
-    if (i < nblk - 1) {
-      const double* Bn = SB + size_t(i + 1) * kk;  // D_i(r,c) = B_{i+1}(c,r)
-      for (int c = 0; c < k; ++c) acc += Bn[r * k + c] * x[(i + 1) * k + c];
-    }
-    if (i < nblk - 2) {
-      const double* An = SA + size_t(i + 2) * kk;
-      for (int c = 0; c < k; ++c) acc += An[r * k + c] * x[(i + 2) * k + c];
-    }
-    y[e] = acc;
+    terms[task] = acc;
   }
+}
+
+// Deterministic sum over the first k <= 32 lanes of warp 0 (fixed shuffle tree).
+__device__ __forceinline__ double lanes_sum(double x) { return warp_sum(x); }
+
+// "Last CTA of the problem" election (threadfence reduction): returns true in every thread of the CTA that
+// arrives last among the nblk block-row CTAs of problem b; that CTA then owns the per-problem epilogue.
+__device__ __forceinline__ bool last_block_of_problem(int* cnt, int nblk) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(cnt, 1);
+    s_last = done == nblk - 1;
+    if (s_last) *cnt = 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
 }
 
 }  // namespace
 
-// Dogleg part 1: Hg = H~ gm, gHg, g.g.
-__global__ void __launch_bounds__(256) k_dogleg_pre(SolverConsts sc, SolverBufs bf) {
-  __shared__ double red[32];
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, n = sc.n;
-  if (!bf.ctl[b].active) return;
-  const size_t hb = size_t(b) * (sc.T + 1) * sc.nq * sc.nq;
-  const double* gm = bf.gm + size_t(b) * n;
-  double* Hg = bf.tmp1 + size_t(b) * n;
-  penta_matvec(sc, bf.SA + hb, bf.SB + hb, bf.SC + hb, gm, Hg, tid, nt);
+// gm = g~ + J~^T lambda (cc:1442), merit = L + h.lambda (cc:1418) and the dogleg scalars gHg = gm.H~ gm,
+// g.g (cc:2157): one CTA per (problem, block row) — the per-problem version of this mat-vec ran 46 us on 64
+// SMs.  Every CTA rebuilds the five blocks of gm its row touches (a few hundred multiply-adds), writes
+// its own block of gm and its partial sums; the last CTA of a problem adds them up in block order.
+__global__ void __launch_bounds__(kRowThreads) k_gm_matvec(SolverConsts sc, SolverBufs bf, int force) {
+  __shared__ double xs[5 * 32], terms[5 * 32];
+  const int nblk = sc.T + 1, b = blockIdx.x / nblk, i = blockIdx.x % nblk;
+  if (!force && !bf.ctl[b].derivs_dirty) return;
+  const int n = sc.n, nh = sc.nh, nu = sc.nu, k = sc.nq, T = sc.T, tid = threadIdx.x, nt = blockDim.x;
+  const size_t hb = size_t(b) * nblk * k * k;
+  const double* gs = bf.gs + size_t(b) * n;
+  const double* lam = bf.lambda + size_t(b) * nh;
+  const bool eq = sc.eq && nh > 0;
+  for (int e = tid; e < 5 * k; e += nt) {
+    const int s = i - 2 + e / k, c = e % k;
+    double val = 0.0;
+    if (s >= 0 && s < nblk) {
+      double acc = 0.0;
+      if (eq) {
+        if (s >= 1)  // rows (s-1, u): Jp[s-1]
+          for (int u = 0; u < nu; ++u) acc += bf.Jp[((size_t(b) * T + (s - 1)) * nu + u) * k + c] * lam[(s - 1) * nu + u];
+        if (s < T)  // rows (s, u): Jt[s]
+          for (int u = 0; u < nu; ++u) acc += bf.Jt[((size_t(b) * T + s) * nu + u) * k + c] * lam[s * nu + u];
+        if (s + 1 < T)  // rows (s+1, u): Jm[s+1]
+          for (int u = 0; u < nu; ++u) acc += bf.Jm[((size_t(b) * T + (s + 1)) * nu + u) * k + c] * lam[(s + 1) * nu + u];
+      }
+      val = eq ? gs[s * k + c] + acc : gs[s * k + c];
+      if (s == i) bf.gm[size_t(b) * n + s * k + c] = val;
+    }
+    xs[e] = val;
+  }
   __syncthreads();
-  double gHg = 0.0, gg = 0.0;
-  for (int e = tid; e < n; e += nt) gHg += gm[e] * Hg[e], gg += gm[e] * gm[e];
-  gHg = block_sum(gHg, red);
-  gg = block_sum(gg, red);
-  if (tid == 0) bf.red[b * 8 + 0] = gHg, bf.red[b * 8 + 1] = gg;
+  block_row_matvec(sc, bf.SA + hb, bf.SB + hb, bf.SC + hb, i, xs, terms, tid, nt);
+  __syncthreads();
+  if (tid < 32) {
+    double gHg = 0.0, gg = 0.0, hl = 0.0;
+    if (tid < k) {
+      const double y = (((terms[tid] + terms[k + tid]) + terms[2 * k + tid]) + terms[3 * k + tid]) + terms[4 * k + tid];
+      const double x = xs[2 * k + tid];
+      gHg = x * y, gg = x * x;
+    }
+    if (eq && i < T && tid < nu) hl = bf.st.h[size_t(b) * nh + i * nu + tid] * lam[i * nu + tid];
+    gHg = lanes_sum(gHg), gg = lanes_sum(gg), hl = lanes_sum(hl);
+    if (tid == 0) {
+      double* pp = bf.part + (size_t(b) * nblk + i) * 4;
+      pp[0] = gHg, pp[1] = gg, pp[2] = hl;
+    }
+  }
+  if (last_block_of_problem(bf.cnt + b, nblk) && tid == 0) {
+    const double* pp = bf.part + size_t(b) * nblk * 4;
+    double gHg = 0.0, gg = 0.0, hl = 0.0;
+    for (int j = 0; j < nblk; ++j) gHg += __ldcg(pp + 4 * j), gg += __ldcg(pp + 4 * j + 1), hl += __ldcg(pp + 4 * j + 2);
+    bf.red[b * 8 + 0] = gHg, bf.red[b * 8 + 1] = gg;
+    bf.merit[b] = eq ? bf.st.cost[b] + hl : bf.st.cost[b];
+  }
 }
 
 // Dogleg part 2: pH = H~^-1(-gm/Delta) = x/Delta with x from k_kkt_solve (cc:2139-2140; the solve is
@@ -73,6 +147,7 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
   const double* D = bf.D + size_t(b) * n;
   double* dq = bf.dq + size_t(b) * n;
   double* dqH = bf.dqH + size_t(b) * n;
+  double* dqs = bf.tmp1 + size_t(b) * n;
   // pU = -(g.g / gHg) g / Delta  (cc:2157)
   double pU2 = 0.0, pH2 = 0.0, a = 0.0, bq = 0.0;
   for (int e = tid; e < n; e += nt) {
@@ -115,6 +190,7 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
     if (sc.scaling) x = D[e] * x;
     const double xh = ph * Delta;  // cc:2152 (dqH is NOT rescaled by D in the reference)
     dq[e] = x, dqH[e] = xh;
+    dqs[e] = sc.scaling ? (1.0 / D[e]) * x : x;  // s = D^-1 dq for the trust ratio (cc:2008)
     dq2 += x * x, dqH2 += xh * xh;
     gdq += sc.scaling ? gm[e] * ((1.0 / D[e]) * x) : gm[e] * x;  // cc:2518-2523
     q2 += q[e] * q[e];
@@ -140,31 +216,52 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
 
 // Trust ratio (cc:1979-2035), acceptance (cc:2550-2553), stats (cc:2586-2598), convergence
 // (cc:2601-2611, 2653-2689) and the Delta update (cc:2613-2622).  `commit`=0 only evaluates rho.
-__global__ void __launch_bounds__(256) k_trust_update(SolverConsts sc, SolverBufs bf, int commit) {
+// One CTA per (problem, block row) computes its rows of H~ s, s = D^-1 dq, and the partial sums of
+// s.H~s, gm.s, h(q+dq).lambda and |h|^2; the last CTA of a problem owns the scalar logic and the commit.
+__global__ void __launch_bounds__(kRowThreads) k_trust_update(SolverConsts sc, SolverBufs bf, int commit) {
+  __shared__ double xs[5 * 32], terms[5 * 32];
   __shared__ double red[32];
   __shared__ int s_accept;
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, n = sc.n, nh = sc.nh;
+  const int nblk = sc.T + 1, b = blockIdx.x / nblk, i = blockIdx.x % nblk;
+  const int tid = threadIdx.x, nt = blockDim.x, n = sc.n, nh = sc.nh, k = sc.nq, nu = sc.nu;
   ProbCtl* ctl = bf.ctl + b;
   if (!ctl->active) return;
-  const size_t hb = size_t(b) * (sc.T + 1) * sc.nq * sc.nq;
-  const double* dq = bf.dq + size_t(b) * n;
-  const double* D = bf.D + size_t(b) * n;
+  const size_t hb = size_t(b) * nblk * k * k;
+  const double* dqs = bf.tmp1 + size_t(b) * n;
   const double* gm = bf.gm + size_t(b) * n;
-  double* dqs = bf.tmp1 + size_t(b) * n;
-  double* Hdq = bf.tmp2 + size_t(b) * n;
-  for (int e = tid; e < n; e += nt) dqs[e] = sc.scaling ? (1.0 / D[e]) * dq[e] : dq[e];
-  __syncthreads();
-  penta_matvec(sc, bf.SA + hb, bf.SB + hb, bf.SC + hb, dqs, Hdq, tid, nt);
-  __syncthreads();
-  double ht = 0.0, gt = 0.0, hl = 0.0, h2 = 0.0;
-  for (int e = tid; e < n; e += nt) ht += dqs[e] * Hdq[e], gt += gm[e] * dqs[e];
-  if (sc.eq)
-    for (int e = tid; e < nh; e += nt) hl += bf.sc.h[size_t(b) * nh + e] * bf.lambda[size_t(b) * nh + e];
-  for (int e = tid; e < nh; e += nt) {
-    const double x = bf.st.h[size_t(b) * nh + e];
-    h2 += x * x;
+  for (int e = tid; e < 5 * k; e += nt) {
+    const int s = i - 2 + e / k;
+    xs[e] = (s >= 0 && s < nblk) ? dqs[s * k + e % k] : 0.0;
   }
-  ht = block_sum(ht, red), gt = block_sum(gt, red), hl = block_sum(hl, red), h2 = block_sum(h2, red);
+  __syncthreads();
+  block_row_matvec(sc, bf.SA + hb, bf.SB + hb, bf.SC + hb, i, xs, terms, tid, nt);
+  __syncthreads();
+  if (tid < 32) {
+    double ht = 0.0, gt = 0.0, hl = 0.0, h2 = 0.0;
+    if (tid < k) {
+      const double y = (((terms[tid] + terms[k + tid]) + terms[2 * k + tid]) + terms[3 * k + tid]) + terms[4 * k + tid];
+      const double x = xs[2 * k + tid];
+      ht = x * y, gt = gm[i * k + tid] * x;
+    }
+    if (i < sc.T && tid < nu) {
+      const size_t e = size_t(b) * nh + i * nu + tid;
+      if (sc.eq) hl = bf.sc.h[e] * bf.lambda[e];
+      h2 = bf.st.h[e] * bf.st.h[e];
+    }
+    ht = lanes_sum(ht), gt = lanes_sum(gt), hl = lanes_sum(hl), h2 = lanes_sum(h2);
+    if (tid == 0) {
+      double* pp = bf.part + (size_t(b) * nblk + i) * 4;
+      pp[0] = ht, pp[1] = gt, pp[2] = hl, pp[3] = h2;
+    }
+  }
+  if (!last_block_of_problem(bf.cnt + b, nblk)) return;
+  double ht = 0.0, gt = 0.0, hl = 0.0, h2 = 0.0;
+  {
+    const double* pp = bf.part + size_t(b) * nblk * 4;
+    for (int j = 0; j < nblk; ++j)
+      ht += __ldcg(pp + 4 * j), gt += __ldcg(pp + 4 * j + 1), hl += __ldcg(pp + 4 * j + 2), h2 += __ldcg(pp + 4 * j + 3);
+  }
+  (void)red;
   const double merit_k = bf.merit[b];
   const double merit_kp = bf.sc.cost[b] + hl;
   const double predicted = -gt - 0.5 * ht;
@@ -199,8 +296,16 @@ __global__ void __launch_bounds__(256) k_trust_update(SolverConsts sc, SolverBuf
       bf.st.a[size_t(b) * T * nv + e] = bf.sc.a[size_t(b) * T * nv + e];
       bf.st.tau[size_t(b) * T * nv + e] = bf.sc.tau[size_t(b) * T * nv + e];
     }
-    for (int e = tid; e < (T + 1) * nv * nq; e += nt)
-      bf.st.Nplus[size_t(b) * (T + 1) * nv * nq + e] = bf.sc.Nplus[size_t(b) * (T + 1) * nv * nq + e];
+    // N+ is a constant pattern except for the 3x4 block of every quaternion joint (k_traj): rows v0..v0+2,
+    // columns q0..q0+3, with v0 = q0 - (number of quaternion joints before it)
+    for (int e = tid; e < (T + 1) * sc.nquat * 12; e += nt) {
+      const int t = e / (sc.nquat * 12), rem = e % (sc.nquat * 12), j = rem / 12, c = (rem % 12) / 3, r = rem % 3;
+      const int q0 = sc.quat_starts[j];
+      int v0 = q0;
+      for (int jj = 0; jj < sc.nquat; ++jj) v0 -= sc.quat_starts[jj] < q0;
+      const size_t o = (size_t(b) * (T + 1) + t) * nv * nq + size_t(q0 + c) * nv + v0 + r;
+      bf.st.Nplus[o] = bf.sc.Nplus[o];
+    }
     for (int e = tid; e < nh; e += nt) bf.st.h[size_t(b) * nh + e] = bf.sc.h[size_t(b) * nh + e];
   }
   // Convergence (cc:2601-2611) needs EvalMeritFunctionGradient of the NEW state, i.e. the
@@ -263,9 +368,13 @@ void launch_clear_dirty(const SolverConsts& sc, const SolverBufs& bf, cudaStream
   g_launch_counter += 1;
 }
 
+void launch_gm_matvec(const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
+  g_launch_counter += 1;
+  k_gm_matvec<<<sc.B*(sc.T + 1), kRowThreads, 0, stream>>>(sc, bf, force ? 1 : 0);
+}
+
 void launch_dogleg(const SolverConsts& sc, const SolverBufs& bf, cudaStream_t stream) {
-  g_launch_counter += 2;
-  k_dogleg_pre<<<sc.B, 256, 0, stream>>>(sc, bf);
+  g_launch_counter += 1;  // Hg, gHg, g.g come with gm (k_gm_matvec, launched with the KKT sweep)
   k_dogleg_post<<<sc.B, 256, 0, stream>>>(sc, bf);
 }
 
@@ -273,7 +382,7 @@ void launch_trust_update(const DevModel& dm, const SolverConsts& sc, const Solve
                          cudaStream_t stream) {
   (void)dm;
   g_launch_counter += 1;
-  k_trust_update<<<sc.B, 256, 0, stream>>>(sc, bf, commit ? 1 : 0);
+  k_trust_update<<<sc.B*(sc.T + 1), kRowThreads, 0, stream>>>(sc, bf, commit ? 1 : 0);
 }
 
 }  // namespace idto

@@ -5,54 +5,70 @@
 
 namespace idto {
 
-// One CTA per problem.  v_t = N+(q_t)(q_t - q_{t-1})/dt, a_t = (v_{t+1} - v_t)/dt.  N+ is the
-// identity pattern (preset at creation) except for the 3x4 quaternion blocks written here.
-__global__ void k_traj(DevModel dm, SolverConsts sc, TrajBuf tb, const double* __restrict__ v_init,
-                       const ProbCtl* __restrict__ ctl, int force) {
-  const int b = blockIdx.x;
-  if (!force && !ctl[b].traj_dirty) return;
-  const int T = sc.T, nq = sc.nq, nv = sc.nv;
-  const double* q = tb.q + size_t(b) * (T + 1) * nq;
-  double* v = tb.v + size_t(b) * (T + 1) * nv;
-  double* a = tb.a + size_t(b) * T * nv;
-  double* Np = tb.Nplus + size_t(b) * (T + 1) * nv * nq;
-  const int* jtype = dm.itab + dm.o_jtype;
-  const int* qs = dm.itab + dm.o_qs;
-  const int* vs = dm.itab + dm.o_vs;
-  for (int idx = threadIdx.x; idx < (T + 1) * dm.nb; idx += blockDim.x) {
-    const int t = idx / dm.nb, k = idx % dm.nb;
-    const int jt = jtype[k], q0 = qs[k], v0 = vs[k];
-    const double* qt = q + size_t(t) * nq + q0;
-    double* vt = v + size_t(t) * nv + v0;
-    if (jt == IDTO_JOINT_QUAT_FLOATING) {
-      V3 col[4];
+namespace {
+
+// Velocity of joint k at step t: v_t = N+(q_t)(q_t - q_{t-1})/dt, v_0 = v_init (cc:178-191).  For a
+// quaternion joint the 3x4 block of N+ is returned in `col` (cc:1633-1647).
+__device__ __forceinline__ void joint_velocity(const SolverConsts& sc, int jt, const double* qt, const double* vinit,
+                                               int t, double* vt, V3* col) {
+  const int nq = sc.nq;
+  if (jt == IDTO_JOINT_QUAT_FLOATING) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) col[c] = quat_nplus_col(qt, c);
+    if (t == 0) {
+      for (int j = 0; j < 6; ++j) vt[j] = vinit[j];
+    } else {
+      const double* qm = qt - nq;
+      V3 acc = {0, 0, 0};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        col[c] = quat_nplus_col(qt, c);
-        double* dst = Np + size_t(t) * nv * nq + size_t(q0 + c) * nv + v0;
-        dst[0] = col[c].x, dst[1] = col[c].y, dst[2] = col[c].z;
+        const double d = qt[c] - qm[c];
+        acc.x += col[c].x * d, acc.y += col[c].y * d, acc.z += col[c].z * d;
       }
-      if (t == 0) {
-        for (int j = 0; j < 6; ++j) vt[j] = v_init[size_t(b) * nv + v0 + j];
-      } else {
-        const double* qm = qt - nq;
-        V3 acc = {0, 0, 0};
+      vt[0] = acc.x / sc.dt, vt[1] = acc.y / sc.dt, vt[2] = acc.z / sc.dt;
+      for (int j = 0; j < 3; ++j) vt[3 + j] = (qt[4 + j] - qm[4 + j]) / sc.dt;
+    }
+  } else {
+    const int n = jt == IDTO_JOINT_PLANAR ? 3 : 1;
+    for (int j = 0; j < n; ++j) vt[j] = t == 0 ? vinit[j] : (qt[j] - qt[j - nq]) / sc.dt;
+  }
+}
+
+}  // namespace
+
+// One thread per (problem, step, joint): v_t, the quaternion block of N+(q_t) (the rest of N+ is the
+// identity pattern preset at creation) and a_t = (v_{t+1} - v_t)/dt (cc:193-202) with v_{t+1} recomputed in
+// place — bit-identical to the stored one — so that no thread waits for another.  (The first version
+// walked a whole problem in one 64-thread CTA: 27 us.)
+__global__ void __launch_bounds__(128) k_traj(DevModel dm, SolverConsts sc, TrajBuf tb, const double* __restrict__ v_init,
+                                              const ProbCtl* __restrict__ ctl, int force) {
+  const int T = sc.T, nq = sc.nq, nv = sc.nv;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= sc.B * (T + 1) * dm.nb) return;
+  const int k = idx % dm.nb, t = (idx / dm.nb) % (T + 1), b = idx / (dm.nb * (T + 1));
+  if (!force && !ctl[b].traj_dirty) return;
+  const int jt = (dm.itab + dm.o_jtype)[k], q0 = (dm.itab + dm.o_qs)[k], v0 = (dm.itab + dm.o_vs)[k];
+  const int njv = jt == IDTO_JOINT_QUAT_FLOATING ? 6 : (jt == IDTO_JOINT_PLANAR ? 3 : 1);
+  const double* qt = tb.q + (size_t(b) * (T + 1) + t) * nq + q0;
+  const double* vi = v_init + size_t(b) * nv + v0;
+  double vt[6], vn[6];
+  V3 col[4];
+  joint_velocity(sc, jt, qt, vi, t, vt, col);
+  double* v = tb.v + (size_t(b) * (T + 1) + t) * nv + v0;
+  for (int j = 0; j < njv; ++j) v[j] = vt[j];
+  if (jt == IDTO_JOINT_QUAT_FLOATING) {
+    double* Np = tb.Nplus + (size_t(b) * (T + 1) + t) * nv * nq;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double d = qt[c] - qm[c];
-          acc.x += col[c].x * d, acc.y += col[c].y * d, acc.z += col[c].z * d;
-        }
-        vt[0] = acc.x / sc.dt, vt[1] = acc.y / sc.dt, vt[2] = acc.z / sc.dt;
-        for (int j = 0; j < 3; ++j) vt[3 + j] = (qt[4 + j] - qm[4 + j]) / sc.dt;
-      }
-    } else {
-      const int n = jt == IDTO_JOINT_PLANAR ? 3 : 1;
-      for (int j = 0; j < n; ++j)
-        vt[j] = t == 0 ? v_init[size_t(b) * nv + v0 + j] : (qt[j] - qt[j - nq]) / sc.dt;
+    for (int c = 0; c < 4; ++c) {
+      double* dst = Np + size_t(q0 + c) * nv + v0;
+      dst[0] = col[c].x, dst[1] = col[c].y, dst[2] = col[c].z;
     }
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < T * nv; idx += blockDim.x) a[idx] = (v[idx + nv] - v[idx]) / sc.dt;
+  if (t < T) {
+    joint_velocity(sc, jt, qt + nq, vi, t + 1, vn, col);
+    double* a = tb.a + (size_t(b) * T + t) * nv + v0;
+    for (int j = 0; j < njv; ++j) a[j] = (vn[j] - vt[j]) / sc.dt;
+  }
 }
 
 // tau_t = ID(q_{t+1}, v_{t+1}, a_t): one G-lane group per (b, t).
@@ -160,7 +176,7 @@ void launch_traj(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b
                  cudaStream_t stream) {
   const TrajBuf& tb = scratch ? bf.sc : bf.st;
   g_launch_counter += 1;
-  k_traj<<<sc.B, 64, 0, stream>>>(dm, sc, tb, bf.v_init, bf.ctl, force ? 1 : 0);
+  k_traj<<<(sc.B * (sc.T + 1) * dm.nb + 127) / 128, 128, 0, stream>>>(dm, sc, tb, bf.v_init, bf.ctl, force ? 1 : 0);
 }
 
 void launch_tau(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch, bool force,

@@ -86,6 +86,8 @@ struct SolverBufs {
   double *X, *S, *rhs;                  // Lagrange multiplier workspace
   double *pH, *dq, *dqH, *tmp1, *tmp2;
   double* red;                          // [B][8] reduction scratch (gHg, gg, ...)
+  double* part;                         // [B][T+1][4] per-block-row partial sums of the row-parallel mat-vecs
+  int* cnt;                             // [B] arrival counters of the "last CTA of the problem" election
   ProbCtl* ctl;
   double* stats;  // [B][stats_cap][IDTO_NUM_STATS]
   int stats_cap;
@@ -108,6 +110,7 @@ void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBuf
 bool launch_kkt_tw2(int kb, const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
 void launch_conv_check(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
 void launch_clear_dirty(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
+void launch_gm_matvec(const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
 void launch_dogleg(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
 void launch_trust_update(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool commit,
                          cudaStream_t stream);
