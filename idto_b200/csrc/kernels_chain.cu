@@ -249,7 +249,7 @@ static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc,
 template <int CG, int NLEV>
 static void launch_tau_chain_cl(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl,
                                 bool force, cudaStream_t stream) {
-  const int threads = 128, groups = threads / CG;
+  const int threads = 64, groups = threads / CG;  // 2560 (b,t) items x CG lanes: small CTAs reach every SM
   const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv, 1) * 8;
   static bool attr_set = false;
   if (!attr_set) {

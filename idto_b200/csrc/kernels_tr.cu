@@ -24,28 +24,33 @@ __device__ __forceinline__ void block_row_matvec(const SolverConsts& sc, const d
     if (term == 0) {
       const double* C = SC + size_t(i) * kk;
       const double* x = xs + 2 * k;
+#pragma unroll 8
       for (int c = 0; c < k; ++c) acc += C[c * k + r] * x[c];
     } else if (term == 1) {
       if (i >= 1) {
         const double* Bm = SB + size_t(i) * kk;
         const double* x = xs + k;
+#pragma unroll 8
         for (int c = 0; c < k; ++c) acc += Bm[c * k + r] * x[c];
       }
     } else if (term == 2) {
       if (i >= 2) {
         const double* Am = SA + size_t(i) * kk;
+#pragma unroll 8
         for (int c = 0; c < k; ++c) acc += Am[c * k + r] * xs[c];
       }
     } else if (term == 3) {
       if (i < nblk - 1) {
         const double* Bn = SB + size_t(i + 1) * kk;  // D_i(r,c) = B_{i+1}(c,r)
         const double* x = xs + 3 * k;
+#pragma unroll 8
         for (int c = 0; c < k; ++c) acc += Bn[r * k + c] * x[c];
       }
     } else {
       if (i < nblk - 2) {
         const double* An = SA + size_t(i + 2) * kk;
         const double* x = xs + 4 * k;
+#pragma unroll 8
         for (int c = 0; c < k; ++c) acc += An[r * k + c] * x[c];
       }
     }
@@ -94,10 +99,13 @@ __global__ void __launch_bounds__(kRowThreads) k_gm_matvec(SolverConsts sc, Solv
       double acc = 0.0;
       if (eq) {
         if (s >= 1)  // rows (s-1, u): Jp[s-1]
+#pragma unroll 6
           for (int u = 0; u < nu; ++u) acc += bf.Jp[((size_t(b) * T + (s - 1)) * nu + u) * k + c] * lam[(s - 1) * nu + u];
         if (s < T)  // rows (s, u): Jt[s]
+#pragma unroll 6
           for (int u = 0; u < nu; ++u) acc += bf.Jt[((size_t(b) * T + s) * nu + u) * k + c] * lam[s * nu + u];
         if (s + 1 < T)  // rows (s+1, u): Jm[s+1]
+#pragma unroll 6
           for (int u = 0; u < nu; ++u) acc += bf.Jm[((size_t(b) * T + (s + 1)) * nu + u) * k + c] * lam[(s + 1) * nu + u];
       }
       val = eq ? gs[s * k + c] + acc : gs[s * k + c];

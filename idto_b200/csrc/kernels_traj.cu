@@ -117,44 +117,64 @@ __global__ void __launch_bounds__(128) k_tau(DevModel dm, SolverConsts sc, TrajB
   }
 }
 
-// Cost (cc:148-176, diagonal weights) and h (cc:1274-1278); one CTA per problem.
-__global__ void k_cost(SolverConsts sc, TrajBuf tb, const double* __restrict__ q_nom,
-                       const double* __restrict__ v_nom, ProbCtl* __restrict__ ctl, int force, int clear_flag) {
+// Cost (cc:148-176, diagonal weights) and h (cc:1274-1278); one CTA per problem, one thread per
+// (step, term) — position, velocity and input cost of a step are independent sums.
+__global__ void __launch_bounds__(256) k_cost(SolverConsts sc, TrajBuf tb, const double* __restrict__ q_nom,
+                                              const double* __restrict__ v_nom, ProbCtl* __restrict__ ctl, int force,
+                                              int clear_flag) {
   __shared__ double red[32];
+  __shared__ double part[3 * 128];
   const int b = blockIdx.x;
   if (!force && !ctl[b].traj_dirty) return;
-  const int T = sc.T, nq = sc.nq, nv = sc.nv;
+  const int T = sc.T, nq = sc.nq, nv = sc.nv, tid = threadIdx.x, nt = blockDim.x;
   const double* q = tb.q + size_t(b) * (T + 1) * nq;
   const double* v = tb.v + size_t(b) * (T + 1) * nv;
   const double* tau = tb.tau + size_t(b) * T * nv;
   const double* qn = q_nom + size_t(b) * (T + 1) * nq;
   const double* vn = v_nom + size_t(b) * (T + 1) * nv;
   double run = 0.0, term = 0.0;
-  for (int t = threadIdx.x; t <= T; t += blockDim.x) {
-    double cq = 0, cv = 0, cu = 0;
-    for (int i = 0; i < nq; ++i) {
-      const double e = q[t * nq + i] - qn[t * nq + i];
-      cq += e * (t < T ? sc.Qq[i] : sc.Qfq[i]) * e;
+  for (int t0 = 0; t0 <= T; t0 += 128) {  // 128 steps per pass
+    __syncthreads();
+    for (int task = tid; task < 3 * 128; task += nt) {
+      const int what = task / 128, t = t0 + task % 128;
+      double c = 0.0;
+      if (t <= T) {
+        if (what == 0) {
+#pragma unroll 4
+          for (int i = 0; i < nq; ++i) {
+            const double e = q[t * nq + i] - qn[t * nq + i];
+            c += e * (t < T ? sc.Qq[i] : sc.Qfq[i]) * e;
+          }
+        } else if (what == 1) {
+#pragma unroll 4
+          for (int i = 0; i < nv; ++i) {
+            const double e = v[t * nv + i] - vn[t * nv + i];
+            c += e * (t < T ? sc.Qv[i] : sc.Qfv[i]) * e;
+          }
+        } else if (t < T) {
+#pragma unroll 4
+          for (int i = 0; i < nv; ++i) c += tau[t * nv + i] * sc.R[i] * tau[t * nv + i];
+        }
+      }
+      part[task] = c;
     }
-    for (int i = 0; i < nv; ++i) {
-      const double e = v[t * nv + i] - vn[t * nv + i];
-      cv += e * (t < T ? sc.Qv[i] : sc.Qfv[i]) * e;
-    }
-    if (t < T) {
-      for (int i = 0; i < nv; ++i) cu += tau[t * nv + i] * sc.R[i] * tau[t * nv + i];
-      run += (cq + cv) + cu;
-    } else {
-      term += cq + cv;
+    __syncthreads();
+    const int t = t0 + tid;
+    if (tid < 128 && t <= T) {
+      if (t < T)
+        run += (part[tid] + part[128 + tid]) + part[256 + tid];
+      else
+        term += part[tid] + part[128 + tid];
     }
   }
   run = block_sum(run, red);
   term = block_sum(term, red);
-  if (threadIdx.x == 0) tb.cost[b] = run * sc.dt + term;
-  for (int idx = threadIdx.x; idx < sc.nh; idx += blockDim.x) {
+  if (tid == 0) tb.cost[b] = run * sc.dt + term;
+  for (int idx = tid; idx < sc.nh; idx += nt) {
     const int t = idx / sc.nu, j = idx % sc.nu;
     tb.h[size_t(b) * sc.nh + idx] = tau[t * nv + sc.unact[j]];
   }
-  if (clear_flag && threadIdx.x == 0) ctl[b].traj_dirty = 0;
+  if (clear_flag && tid == 0) ctl[b].traj_dirty = 0;
 }
 
 template <int G>
@@ -185,7 +205,7 @@ void launch_tau(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf
   if (use_chain_kernels(dm)) {
     launch_tau_chain(dm, sc, tb, bf.ctl, force, stream);
     g_launch_counter += 1;
-    k_cost<<<sc.B, 64, 0, stream>>>(sc, tb, bf.q_nom, bf.v_nom, bf.ctl, force ? 1 : 0, scratch ? 0 : 1);
+    k_cost<<<sc.B, 256, 0, stream>>>(sc, tb, bf.q_nom, bf.v_nom, bf.ctl, force ? 1 : 0, scratch ? 0 : 1);
     return;
   }
   switch (dm.group) {
@@ -196,7 +216,7 @@ void launch_tau(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf
     default: launch_tau_g<32>(dm, sc, tb, bf.ctl, force, stream); break;
   }
   g_launch_counter += 1;
-  k_cost<<<sc.B, 64, 0, stream>>>(sc, tb, bf.q_nom, bf.v_nom, bf.ctl, force ? 1 : 0, scratch ? 0 : 1);
+  k_cost<<<sc.B, 256, 0, stream>>>(sc, tb, bf.q_nom, bf.v_nom, bf.ctl, force ? 1 : 0, scratch ? 0 : 1);
 }
 
 }  // namespace idto
