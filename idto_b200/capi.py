@@ -72,6 +72,7 @@ def lib():
         L.idto_get.argtypes = [H, ctypes.c_char_p, _D]
         L.idto_solve.argtypes = [H, ctypes.c_int, _I, _I, _D]
         L.idto_resolve_async.argtypes = [H, ctypes.c_int] + [ctypes.c_void_p] * 8 + [_I, ctypes.c_void_p]
+        L.idto_mpc_advance.argtypes = [H, _D, _D, _D, _D]
         L.idto_fence.argtypes = [H]
         L.idto_flush_l2.argtypes = [H, ctypes.c_void_p, ctypes.c_size_t]
         L.idto_launch_count.argtypes = [H]
@@ -169,6 +170,15 @@ class BatchSolver:
         """End-to-end MPC re-solve: arguments are raw host pointers (ints) of pinned buffers or None."""
         _check(lib().idto_resolve_async(self.h, int(max_iterations), q_guess, q_init, v_init, q_nom, v_nom, q_out,
                                         v_out, tau_out, None, stats_out))
+
+    def mpc_advance(self, elapsed, q0, v0, q_nom_selector=None):
+        """Device-side MPC shell between two re-solves (examples/mpc_controller.cc:43-98): spline-shifted
+        guess, shifted nominal trajectory, new initial conditions.  elapsed: scalar or [batch] seconds."""
+        el = np.ascontiguousarray(np.broadcast_to(np.asarray(elapsed, float), (self.B,)))
+        q0 = self._arr(q0, (self.B, self.nq))
+        v0 = self._arr(v0, (self.B, self.nv))
+        sel = None if q_nom_selector is None else np.ascontiguousarray(np.asarray(q_nom_selector, float).reshape(self.nq))
+        _check(lib().idto_mpc_advance(self.h, _p(el), _p(q0), _p(v0), None if sel is None else _p(sel)))
 
     def fence(self):
         _check(lib().idto_fence(self.h))

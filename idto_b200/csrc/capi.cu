@@ -71,6 +71,7 @@ struct idto_solver_s {
   idto_params params;
   // mutable per-batch problem data
   double *q_init, *v_init, *q_nom, *v_nom;
+  double* mpc_in = nullptr;  // staging of idto_mpc_advance inputs: [B] elapsed | [B][nq] q0 | [B][nv] v0 | [nq] selector
   long launches0 = 0;
   bool profile = false;
   std::map<std::string, std::vector<ProfEvent>> prof;
@@ -608,6 +609,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   alloc(&bf.pH, nvar), alloc(&bf.dq, nvar), alloc(&bf.dqH, nvar), alloc(&bf.tmp1, nvar), alloc(&bf.tmp2, nvar);
   alloc(&bf.red, size_t(B) * 8);
   alloc(&bf.part, size_t(B) * (T + 1) * 4);
+  alloc(&s->mpc_in, size_t(B) * (1 + nq + nv) + nq);
   ok = ok && A.get(&bf.cnt, B) == cudaSuccess;
   ok = ok && A.get(&bf.ctl, B) == cudaSuccess && A.get(&bf.status, 1) == cudaSuccess;
   if (!ok) {
@@ -786,8 +788,8 @@ long idto_field_size(idto_solver_t s, const char* field) {
   const SolverConsts& c = s->sc;
   const std::string f(field);
   const long T = c.T, nq = c.nq, nv = c.nv;
-  if (f == "q") return (T + 1) * nq;
-  if (f == "v") return (T + 1) * nv;
+  if (f == "q" || f == "q_nom") return (T + 1) * nq;
+  if (f == "v" || f == "v_nom") return (T + 1) * nv;
   if (f == "a" || f == "tau") return T * nv;
   if (f == "Nplus") return (T + 1) * nv * nq;
   if (f == "cost" || f == "merit" || f == "dq_active" || f == "rho" || f == "delta") return 1;
@@ -815,6 +817,8 @@ int idto_get(idto_solver_t s, const char* field, double* out) {
   IDTO_CUDA_CHECK(cudaStreamSynchronize(s->stream));
   const double* src = nullptr;
   if (f == "q") src = bf.st.q;
+  else if (f == "q_nom") src = bf.q_nom;
+  else if (f == "v_nom") src = bf.v_nom;
   else if (f == "v") src = bf.st.v;
   else if (f == "a") src = bf.st.a;
   else if (f == "tau") src = bf.st.tau;
@@ -1007,6 +1011,29 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
     }
   }
   (void)iters_out;
+  return IDTO_OK;
+}
+
+int idto_mpc_advance(idto_solver_t s, const double* elapsed, const double* q0, const double* v0,
+                     const double* q_nom_selector) {
+  if (!s || !elapsed || !q0 || !v0) return IDTO_ERR_INVALID_ARG;
+  const SolverConsts& c = s->sc;
+  const size_t B = c.B;
+  use_main(s);
+  double* d_el = s->mpc_in;
+  double* d_q0 = d_el + B;
+  double* d_v0 = d_q0 + B * c.nq;
+  double* d_sel = d_v0 + B * c.nv;
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(d_el, elapsed, B * 8, cudaMemcpyHostToDevice, s->stream));
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(d_q0, q0, B * c.nq * 8, cudaMemcpyHostToDevice, s->stream));
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(d_v0, v0, B * c.nv * 8, cudaMemcpyHostToDevice, s->stream));
+  if (q_nom_selector)
+    IDTO_CUDA_CHECK(cudaMemcpyAsync(d_sel, q_nom_selector, size_t(c.nq) * 8, cudaMemcpyHostToDevice, s->stream));
+  if (int rc = launch_mpc_advance(c, s->bf, d_el, d_q0, d_v0, q_nom_selector ? d_sel : nullptr, s->q_init, s->v_init,
+                                  s->q_nom, s->stream)) {
+    set_last_error("idto_mpc_advance: horizon too long for the spline workspace");
+    return rc;
+  }
   return IDTO_OK;
 }
 

@@ -114,6 +114,11 @@ void launch_gm_matvec(const SolverConsts& sc, const SolverBufs& b, bool force, c
 void launch_dogleg(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
 void launch_trust_update(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool commit,
                          cudaStream_t stream);
+// MPC shell: spline-shifted guess, shifted nominal trajectory, new initial conditions (kernels_mpc.cu); all
+// pointers are device pointers ([B] elapsed seconds, [B][nq] q0, [B][nv] v0, [nq] selector or null)
+int launch_mpc_advance(const SolverConsts& sc, const SolverBufs& b, const double* elapsed, const double* q0,
+                       const double* v0, const double* selector, double* q_init, double* v_init, double* q_nom,
+                       cudaStream_t stream);
 int partials_smem_bytes(const DevModel& dm, int nq);
 bool chain_supported(const DevModel& dm);
 void launch_partials_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,

@@ -177,7 +177,7 @@ int idto_eval_trust_ratio(idto_solver_t s);
 /* Device → host mirror of a named cache entry for all batch elements.
  * `out` must hold idto_field_size(field) * batch doubles.  Names:
  *  q v a tau Nplus cost h dtau_dqm dtau_dqt dtau_dqp g H_A H_B H_C D Hs_A Hs_B Hs_C gs
- *  J lambda merit gm dq dqH dq_active rho delta
+ *  J lambda merit gm dq dqH dq_active rho delta q_nom v_nom
  * Layouts follow the reference containers: per time step, column-major blocks. */
 long idto_field_size(idto_solver_t s, const char* field);
 int idto_get(idto_solver_t s, const char* field, double* out);
@@ -205,6 +205,17 @@ int idto_resolve_async(idto_solver_t s, int max_iterations,
                        double* q_out, double* v_out, double* tau_out,
                        int* iters_out, double* stats_out);
 int idto_synchronize(idto_solver_t s);
+/* MPC shell between two re-solves, on the device (ModelPredictiveController::UpdateAbstractState,
+ * examples/mpc_controller.cc:43-98; python_examples/mpc_utils.py:183-217), for every batch element b:
+ *   q_guess_i = spline(elapsed[b] + i dt), i = 1..T, where spline is the C2 cubic (not-a-knot) interpolant of
+ *               the current q_0..q_T (PiecewisePolynomial::CubicWithContinuousSecondDerivatives,
+ *               mpc_controller.cc:129-137), evaluation clamped to [0, T dt];  q_guess_0 = q0[b];
+ *   q_nom_t  += q_nom_selector o (q0[b] - q_nom_0)   (mpc_controller.cc:62-69; NULL: no shift);
+ *   ResetInitialConditions(q0[b], v0[b]); all cache entries stale.
+ * Host pointers: elapsed [batch], q0 [batch][nq], v0 [batch][nv], q_nom_selector [nq] (0/1 as doubles).
+ * Asynchronous on the solver's stream; follow with idto_resolve_async(..., all inputs NULL). */
+int idto_mpc_advance(idto_solver_t s, const double* elapsed, const double* q0, const double* v0,
+                     const double* q_nom_selector);
 /* Stream-ordering point without a host wait: everything enqueued so far (on the internal sub-batch
  * streams too) is ordered before whatever the caller enqueues next on the solver's stream, e.g. a
  * CUDA event record. */
