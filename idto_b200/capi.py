@@ -124,6 +124,8 @@ class BatchSolver:
     def __init__(self, model: Model, time_step: float, prob: ProblemDefinition, params: SolverParameters,
                  batch: int = 1):
         self.model, self.prob, self.params, self.B = model, prob, params, int(batch)
+        if getattr(params, "unsupported", None):  # options outside the CUDA hot path (yaml_config.SetSolverParameters)
+            raise IdtoError("unsupported: " + ", ".join(params.unsupported) + " (no CPU fallback)")
         self.T, self.nq, self.nv = prob.num_steps, model.baked.nq, model.baked.nv
         pd, self._keep = prob.to_c(time_step, self.nq, self.nv)
         pc = params.to_c()
