@@ -181,6 +181,7 @@ void make_view(const idto_solver_s* s, int b0, int nb, SolverConsts* scv, Solver
   v.Jm += o * T * nuq, v.Jt += o * T * nuq, v.Jp += o * T * nuq;
   v.FY += o * T1 * kb * kb, v.FZ += o * T1 * kb * kb, v.X += o * T1 * kb, v.rhs += o * nh;
   v.pH += o * n, v.dq += o * n, v.dqH += o * n, v.tmp1 += o * n, v.tmp2 += o * n, v.red += o * 8, v.part += o * T1 * 4, v.cnt += o;
+  if (v.stash) v.stash += o * T * size_t(s->model->dm.nb) * 48;
   v.ctl += o;
   if (v.stats) v.stats += o * size_t(v.stats_cap) * IDTO_NUM_STATS;
   *bfv = v;
@@ -478,6 +479,38 @@ int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
     for (int k = 0; k < nb; ++k)  // multi-dof joints must hang off the world (R_WF == R_PF in the backward pass)
       if ((d->joint_type[k] == IDTO_JOINT_PLANAR || d->joint_type[k] == IDTO_JOINT_QUAT_FLOATING) && d->parent[k] >= 0)
         dm.chain_ok = 0;
+    // column split (see DevModel::npath)
+    std::vector<int> pathcols, fullcols;
+    {
+      const bool enable = dm.chain_ok && !(std::getenv("IDTO_PATH_COLS") && std::atoi(std::getenv("IDTO_PATH_COLS")) == 0);
+      for (int i = 0; i < d->nq; ++i) {
+        const int k = qowner[i];
+        bool ok = enable && (d->joint_type[k] == IDTO_JOINT_REVOLUTE || d->joint_type[k] == IDTO_JOINT_PRISMATIC);
+        std::vector<char> in_sub(nb, 0);
+        int ndown = 0;
+        for (int bdy = k; ok;) {  // the subtree must be a chain of 1-dof joints, at most 4 bodies long
+          in_sub[bdy] = 1;
+          ++ndown;
+          const int jt = d->joint_type[bdy];
+          if (jt != IDTO_JOINT_REVOLUTE && jt != IDTO_JOINT_PRISMATIC) ok = false;
+          if (nchild[bdy] > 1 || ndown > 4) ok = false;
+          if (nchild[bdy] == 0) break;
+          bdy = child[size_t(0) * nbp + bdy];
+        }
+        int nup = 0;
+        for (int a = d->parent[k]; a >= 0; a = d->parent[a]) ++nup;
+        if (nup > 7) ok = false;
+        for (int ip = 0; ip < np && ok; ++ip) {  // contact partners of subtree bodies must be world-anchored
+          const int bA = d->geom_body[d->pair_geomA[ip]], bB = d->geom_body[d->pair_geomB[ip]];
+          const bool sA = bA >= 0 && in_sub[bA], sB = bB >= 0 && in_sub[bB];
+          if ((sA && bB >= 0) || (sB && bA >= 0)) ok = false;
+        }
+        (ok ? pathcols : fullcols).push_back(i);
+      }
+    }
+    dm.npath = int(pathcols.size()), dm.nfull = int(fullcols.size());
+    dm.o_pathcols = push_i(pathcols.data(), dm.npath, std::max(dm.npath, 1));
+    dm.o_fullcols = push_i(fullcols.data(), dm.nfull, std::max(dm.nfull, 1));
     dm.o_levbody = push_i(levbody.data(), kMaxLevels * CG, kMaxLevels * CG);
     dm.o_levcross = push_i(levcross.data(), kMaxLevels, kMaxLevels);
     dm.o_plane = push_i(plane.data(), nb, nbp);
@@ -609,6 +642,8 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   alloc(&bf.pH, nvar), alloc(&bf.dq, nvar), alloc(&bf.dqH, nvar), alloc(&bf.tmp1, nvar), alloc(&bf.tmp2, nvar);
   alloc(&bf.red, size_t(B) * 8);
   alloc(&bf.part, size_t(B) * (T + 1) * 4);
+  bf.stash = nullptr;
+  if (m->dm.npath > 0) alloc(&bf.stash, size_t(B) * T * m->dm.nb * 48);
   alloc(&s->mpc_in, size_t(B) * (1 + nq + nv) + nq);
   ok = ok && A.get(&bf.cnt, B) == cudaSuccess;
   ok = ok && A.get(&bf.ctl, B) == cudaSuccess && A.get(&bf.status, 1) == cudaSuccess;

@@ -92,11 +92,19 @@ enum { kEvalFull = 0, kEvalSharedPose = 1, kEvalSharedPoseNoBias = 2, kEvalPoseO
 //   MODE kEvalSharedPoseNoBias: tau = M(q) a only (no gravity / damping / contact / velocity terms)
 //   MODE kEvalPoseOnly:       pose + contact geometry of q into `Po`, nothing else
 // q, v, a: global rows of this (problem, time).  tau_out: [nv] doubles (shared or global).
-template <int CG, int NLEV, int MODE>
+// STASH: additionally write the per-body record of this evaluation (kStash* layout below) to `stash`
+// ([nb][kStashDoubles] doubles in global memory) for the single-lane path evaluations of kernels_path.cu.
+constexpr int kStashDoubles = 48;
+enum { kStR = 0, kStP = 9, kStRF = 12, kStW = 21, kStV = 24, kStAl = 27, kStAc = 30, kStFpre = 33, kStFtot = 39,
+       kStAX = 45 };
+__device__ __forceinline__ void stash_V(double* rec, int off, V3 x) { rec[off] = x.x, rec[off + 1] = x.y, rec[off + 2] = x.z; }
+__device__ __forceinline__ V3 unstash_V(const double* rec, int off) { return {rec[off], rec[off + 1], rec[off + 2]}; }
+
+template <int CG, int NLEV, int MODE, bool STASH = false>
 __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& sc, const PoseSmem& Po,
                                            const EvalSmem& S, int c, const double* __restrict__ q,
                                            const double* __restrict__ v, const double* __restrict__ a,
-                                           const Perturb& pt, double* tau_out) {
+                                           const Perturb& pt, double* tau_out, double* stash = nullptr) {
   const SModel& M = C.M;
   const int nb = M.nb;
   const int gbase = (threadIdx.x & 31) / CG * CG;
@@ -257,6 +265,13 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
         store_V(S.F + 3 * nb, nb, b, f);
         store_V(S.P, nb, b, p_WB);
         store_V(S.AX, nb, b, mul(R_WF, axis));
+        if (STASH) {
+          double* rec = stash + size_t(b) * kStashDoubles;
+#pragma unroll
+          for (int e = 0; e < 9; ++e) rec[kStR + e] = R_WB.m[e], rec[kStRF + e] = R_WF.m[e];
+          stash_V(rec, kStP, p_WB), stash_V(rec, kStW, w), stash_V(rec, kStV, vv);
+          stash_V(rec, kStAl, al), stash_V(rec, kStAc, ac), stash_V(rec, kStAX, mul(R_WF, axis));
+        }
       }
     }
   }
@@ -365,6 +380,7 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
           }
         Tt = Tt - Ft, Tf = Tf - Ff;
       }
+      if (STASH) stash_V(stash + size_t(b) * kStashDoubles, kStFpre, Tt), stash_V(stash + size_t(b) * kStashDoubles, kStFpre + 3, Tf);
       const int nchild = M.nchild[b];
       for (int ci = 0; ci < nchild; ++ci) {
         const int ch = M.child[ci * M.nbp + b];
@@ -375,6 +391,7 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
       }
       store_V(S.F, nb, b, Tt);
       store_V(S.F + 3 * nb, nb, b, Tf);
+      if (STASH) stash_V(stash + size_t(b) * kStashDoubles, kStFtot, Tt), stash_V(stash + size_t(b) * kStashDoubles, kStFtot + 3, Tf);
       const int jtype = M.jtype[b], v0 = M.vs[b];
       if (jtype == IDTO_JOINT_REVOLUTE) {
         tau_out[v0] += dot(load_V(S.AX, nb, b), Tt);

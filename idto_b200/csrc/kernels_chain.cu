@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   extern __shared__ __align__(16) unsigned char smem[];
   const int T = sc.T, nq = sc.nq, nv = sc.nv;
   const int g = threadIdx.x / CG, c = threadIdx.x % CG;
-  const int slot = g / nq, i = g % nq;
+  const int ncol = dm.nfull;  // columns differentiated here (the path columns go to kernels_path.cu)
+  const int slot = g / ncol, ii = g % ncol;
+  const int i = (dm.itab + dm.o_fullcols)[ii];
   const int sg = blockIdx.x * slots + slot;
   const bool valid = (slot < slots) && (sg < sc.B * T);
   const int b = valid ? sg / T : 0;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   const int sslot = valid ? slot : slots;  // padding groups write their (discarded) poses to a dummy slot
   const PoseSmem PB = make_cpose(dm, base + size_t(sslot) * 2 * pd);
   const PoseSmem PC = make_cpose(dm, base + size_t(sslot) * 2 * pd + pd);
-  const int gidx = slot < slots ? g : slots * nq;  // padding groups share one dummy area
+  const int gidx = slot < slots ? g : slots * ncol;  // padding groups share one dummy area
   double* gbase = base + size_t(slots + 1) * 2 * pd + size_t(gidx) * gd;
   const EvalSmem S = make_ceval(dm, gbase);
   const PoseSmem PA = make_cpose_private(dm, gbase + ceval_doubles(dm));
@@ -116,15 +118,15 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
 
   // ---- phase 0: shared poses of q_{t+1} (even groups) and q_{t+2} (odd groups), first warp(s) of a slot ----
   {
-    const bool mine = valid && i < 2 * CG && i < nq;  // enough groups to fill the warp that holds groups 0, 1
+    const bool mine = valid && ii < 2 * CG && ii < ncol;  // enough groups to fill the warp that holds groups 0, 1
     if (__any_sync(0xffffffffu, mine)) {
       Perturb none = pt;
       none.owner = -1;
-      if ((i & 1) == 0 || nq == 1)
+      if ((ii & 1) == 0 || ncol == 1)
         chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PB, S, c, qB + size_t(tp1) * nq, vB, aB, none, T0);
       else
         chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PC, S, c, qB + size_t(tp2) * nq, vB, aB, none, T0);
-      if (nq == 1) chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PC, S, c, qB + size_t(tp2) * nq, vB, aB, none, T0);
+      if (ncol == 1) chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PC, S, c, qB + size_t(tp2) * nq, vB, aB, none, T0);
     }
   }
 
@@ -188,8 +190,10 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
 }
 
 // tau_t = ID(q_{t+1}, v_{t+1}, a_t): one CG-lane group per (b, t).
-template <int CG, int NLEV>
-__global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc, TrajBuf tb,
+// STASH: the same evaluation for the state trajectory, gated on derivs_dirty, that writes the per-body records
+// for the path columns (kernels_path.cu) instead of tau.
+template <int CG, int NLEV, bool STASH = false>
+__global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc, TrajBuf tb, double* __restrict__ stash,
                                                    const ProbCtl* __restrict__ ctl, int force) {
   extern __shared__ __align__(16) unsigned char smem[];
   int* si = reinterpret_cast<int*>(smem);
@@ -208,14 +212,17 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
   const int item = blockIdx.x * groups + grp;
   const bool in_range = item < sc.B * T;
   const int b = in_range ? item / T : 0, t = in_range ? item % T : 0;
-  const bool live = in_range && (force || ctl[b].traj_dirty);
+  const bool live = in_range && (force || (STASH ? ctl[b].derivs_dirty : ctl[b].traj_dirty));
   Perturb none;
   none.owner = -1, none.local = 0, none.sl = 0, none.quatcol = false;
   none.dq = none.cv = none.ca = 0.0, none.uv = none.ua = 1.0, none.nv3 = none.na3 = {0, 0, 0};
-  chain_eval<CG, NLEV, kEvalFull>(C, sc, PA, S, c, tb.q + (size_t(b) * (T + 1) + t + 1) * nq,
-                                  tb.v + (size_t(b) * (T + 1) + t + 1) * nv, tb.a + (size_t(b) * T + t) * nv, none, T0);
+  // (groups that are not live write their records to the slot of item (0, 0): same values as its owner)
+  double* rec = STASH ? stash + (size_t(live ? b : 0) * T + (live ? t : 0)) * dm.nb * kStashDoubles : nullptr;
+  chain_eval<CG, NLEV, kEvalFull, STASH>(C, sc, PA, S, c, tb.q + (size_t(live ? b : 0) * (T + 1) + (live ? t : 0) + 1) * nq,
+                                         tb.v + (size_t(live ? b : 0) * (T + 1) + (live ? t : 0) + 1) * nv,
+                                         tb.a + (size_t(live ? b : 0) * T + (live ? t : 0)) * nv, none, T0, rec);
   __syncwarp();
-  if (live) {
+  if (live && !STASH) {
     double* tau = tb.tau + (size_t(b) * T + t) * nv;
     for (int r = c; r < nv; r += CG) tau[r] = T0[r];
   }
@@ -225,7 +232,10 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
 template <int CG, int NLEV>
 static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
                                      cudaStream_t stream) {
-  const ChainLayout L = chain_layout(dm, sc.nq, sc.nv, sc.method == IDTO_GRAD_CENTRAL4 ? 3 : 2);
+  launch_stash_chain(dm, sc, bf, force, stream);  // base records for the path columns (no-op without any)
+  launch_partials_path(dm, sc, bf, force, stream);
+  if (dm.nfull == 0) return;
+  const ChainLayout L = chain_layout(dm, dm.nfull, sc.nv, sc.method == IDTO_GRAD_CENTRAL4 ? 3 : 2);
   const int grid = (sc.B * sc.T + L.slots - 1) / L.slots;
   g_launch_counter += 1;
 #define IDTO_LAUNCH_PC(METHOD)                                                                                   \
@@ -257,7 +267,22 @@ static void launch_tau_chain_cl(const DevModel& dm, const SolverConsts& sc, cons
     attr_set = true;
   }
   g_launch_counter += 1;
-  k_tau_chain<CG, NLEV><<<(sc.B * sc.T + groups - 1) / groups, threads, smem, stream>>>(dm, sc, tb, ctl, force);
+  k_tau_chain<CG, NLEV><<<(sc.B * sc.T + groups - 1) / groups, threads, smem, stream>>>(dm, sc, tb, nullptr, ctl, force);
+}
+
+template <int CG, int NLEV>
+static void launch_stash_chain_cl(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
+                                  cudaStream_t stream) {
+  const int threads = 64, groups = threads / CG;
+  const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv, 1) * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_tau_chain<CG, NLEV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    attr_set = true;
+  }
+  g_launch_counter += 1;
+  k_tau_chain<CG, NLEV, true><<<(sc.B * sc.T + groups - 1) / groups, threads, smem, stream>>>(dm, sc, bf.st, bf.stash,
+                                                                                             bf.ctl, force);
 }
 
 // Instantiated (lanes per evaluation, padded tree depth) pairs; anything else falls back to the
@@ -290,6 +315,11 @@ bool chain_supported(const DevModel& dm) {
 void launch_partials_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
                            cudaStream_t stream) {
   IDTO_CHAIN_DISPATCH(launch_partials_chain_cl, dm, sc, bf, force, stream)
+}
+void launch_stash_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
+                        cudaStream_t stream) {
+  if (dm.npath == 0) return;
+  IDTO_CHAIN_DISPATCH(launch_stash_chain_cl, dm, sc, bf, force, stream)
 }
 void launch_tau_chain(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl, bool force,
                       cudaStream_t stream) {

@@ -34,6 +34,10 @@ struct DevModel {
   int cgroup, nchains, ngb, ngd;  // ngb: bodies carrying geometry, ngd: geometries on moving bodies
   int chain_ok;                   // the chain-lane kernels support this model
   int cg_res;                     // per-group smem stride is padded to cg_res (mod 16 doubles): bank spread
+  // Column split of the ID partials: "path" columns (1-dof joint whose subtree is a simple chain touching only
+  // world-anchored geometry) are differentiated by single-lane subtree evaluations (kernels_path.cu), the rest
+  // ("full" columns) by full evaluations (kernels_chain.cu).  npath + nfull == nq.
+  int npath, nfull, o_pathcols, o_fullcols;
   double gx, gy, gz;
   // int table offsets (in ints)
   int o_parent, o_jtype, o_qs, o_vs, o_level, o_nchild, o_child, o_flags, o_qowner, o_gbody, o_gtype, o_pA, o_pB;
@@ -86,6 +90,7 @@ struct SolverBufs {
   double *X, *S, *rhs;                  // Lagrange multiplier workspace
   double *pH, *dq, *dqH, *tmp1, *tmp2;
   double* red;                          // [B][8] reduction scratch (gHg, gg, ...)
+  double* stash;                        // [B][T][nb][48] per-body records of the base evaluations (kernels_path.cu)
   double* part;                         // [B][T+1][4] per-block-row partial sums of the row-parallel mat-vecs
   int* cnt;                             // [B] arrival counters of the "last CTA of the problem" election
   ProbCtl* ctl;
@@ -123,6 +128,11 @@ int partials_smem_bytes(const DevModel& dm, int nq);
 bool chain_supported(const DevModel& dm);
 void launch_partials_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
                            cudaStream_t stream);
+// single-lane subtree evaluations for the path columns (after launch_stash_chain filled bf.stash)
+void launch_partials_path(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
+                          cudaStream_t stream);
+void launch_stash_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
+                        cudaStream_t stream);
 void launch_tau_chain(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl, bool force,
                       cudaStream_t stream);
 bool use_chain_kernels(const DevModel& dm);  // chain-lane kernels unless IDTO_DYNAMICS=group or unsupported
