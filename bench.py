@@ -11,8 +11,10 @@ of each of the `batch` = 64 independent warm-started MPC problems resident on a 
 re-plan (`mpc_iters: 1`).  Every step starts from a state whose caches are stale (as after the MPC
 guess shift), so no step is a cheap "rejected step" replay.
   value = problems * steps / device time, inputs resident in HBM.
-  e2e   = the same through the public C-ABI call with pinned HOST buffers: per step H2D of the
-          guess + initial conditions and D2H of the solution and stats.
+  e2e   = the same through the public C-ABI calls an MPC loop makes (ModelPredictiveController::
+          UpdateAbstractState, examples/mpc_controller.cc:43-98) with pinned HOST buffers: per step H2D of
+          the measured state (q0, v0, elapsed time) into idto_mpc_advance, which shifts the previous
+          solution on the device, then the re-solve and D2H of the solution trajectory and stats.
 """
 from __future__ import annotations
 
@@ -142,7 +144,7 @@ def main():
                           f"batch={args.batch} independent MPC re-solves per GPU, 1 iteration per step, "
                           f"gradients={args.method}_differences, equality_constraints=on, scaling=double_sqrt",
               "model": "mini_cheetah_with_ground", "nq": m.nq, "nv": m.nv, "T": T, "batch_per_gpu": args.batch,
-              "l2": "flushed before every step (256 MB memset in stream order, inside the timed region)"}
+              "l2": "flushed before every step (160 MiB memset in stream order, inside the timed region; L2 = 126 MB)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -184,9 +186,9 @@ def main():
     # ---- device-resident throughput ----------------------------------------------------------
     # K re-solves back to back, timed with ONE CUDA-event pair on the solver's stream around the whole
     # region (idto_fence orders the internal sub-batch streams against the events).  L2 hygiene: before
-    # every step a 256 MB scratch buffer is overwritten in stream order INSIDE the timed region (the
+    # every step a 160 MiB scratch buffer is overwritten in stream order INSIDE the timed region (the
     # per-step working set, ~110 MB of bands / KKT sweep / partials, would otherwise fit the 126 MB L2).
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")  # L2 is 126 MB
 
     def step_resident():
         gs.flush_l2(flush.data_ptr(), flush.numel())
@@ -217,22 +219,22 @@ def main():
 
     # ---- end to end through the C ABI with pinned host buffers ------------------------------------
     T1 = T + 1
-    hq = torch.from_numpy(qg.copy()).pin_memory()
     hq0, hv0 = torch.from_numpy(q0.copy()).pin_memory(), torch.from_numpy(v0.copy()).pin_memory()
+    hel = torch.zeros(B, dtype=torch.float64).pin_memory()  # elapsed time since the stored solution: 0 keeps the
+    # workload of the resident arm (guess = previous solution at its knots; q_guess[0] = the measured q0)
     oq = torch.empty((B, T1, m.nq), dtype=torch.float64).pin_memory()
     ov = torch.empty((B, T1, m.nv), dtype=torch.float64).pin_memory()
     ot = torch.empty((B, T, m.nv), dtype=torch.float64).pin_memory()
     ost = torch.empty((B, 1, NUM_STATS), dtype=torch.float64).pin_memory()
-    hq_np, oq_np = hq.numpy(), oq.numpy()
-    h2d = (hq.numel() + hq0.numel() + hv0.numel()) * 8
+    hq0_np, hv0_np, hel_np = hq0.numpy(), hv0.numpy(), hel.numpy()
+    h2d = (hq0.numel() + hv0.numel() + hel.numel()) * 8
     d2h = (oq.numel() + ov.numel() + ot.numel() + ost.numel()) * 8
 
     def step_e2e():
         gs.flush_l2(flush.data_ptr(), flush.numel())
-        gs.resolve_async(1, q_guess=hq.data_ptr(), q_init=hq0.data_ptr(), v_init=hv0.data_ptr(),
-                         q_out=oq.data_ptr(), v_out=ov.data_ptr(), tau_out=ot.data_ptr(), stats_out=ost.data_ptr())
+        gs.mpc_advance(hel_np, hq0_np, hv0_np)  # H2D of the measured state; guess shifted on the device
+        gs.resolve_async(1, q_out=oq.data_ptr(), v_out=ov.data_ptr(), tau_out=ot.data_ptr(), stats_out=ost.data_ptr())
         gs.synchronize()
-        np.copyto(hq_np, oq_np)  # the next re-solve starts from the previous solution (MPC warm start)
 
     for _ in range(warmup):
         step_e2e()
@@ -272,7 +274,7 @@ def main():
             traffic = json.load(f).get(f"id_partials_{args.method}")
     except OSError:
         pass
-    roofline = {"kernel": "k_partials_chain", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "id_partials stage: k_tau_chain<stash> + k_partials_path + k_partials_chain", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
                 "avg_launch_ms": stage_ms["id_partials"],
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",

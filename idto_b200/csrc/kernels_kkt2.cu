@@ -59,6 +59,10 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kLuWarps = 4;   // warps that eliminate (each holds G and 1/kLuWarps of the right-hand sides)
 constexpr int kThreads = 256;
 
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+
 // 1/x to ~1 ulp without the division subroutine: MUFU.RCP64H seed (>= 20 bits) + two Newton steps.
 __device__ __forceinline__ double fast_rcp(double x) {
   double y;
@@ -541,12 +545,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   double* xs = sm + 3 * kSlot;    // [2][LD] the two most recent solution blocks
   const int istart = dir == 0 ? mid - 1 : mid + 2, iend = dir == 0 ? -1 : N + 1;
   const int nrows = dir == 0 ? mid : N - mid - 1;
+  // cp.async (LDGSTS): the loader threads do not wait for their loads, the ring slot of row it+2 fills while
+  // rows it and it+1 are consumed (with plain loads every row paid an L2 round trip before its barrier)
   auto fetch = [&](int it, int t0, int nt) {
-    if (it >= nrows) return;
-    const int i = istart - sgn * it;
-    double* dst = ring + (it % 3) * kSlot;
-    for (int e = t0; e < kk; e += nt) dst[e] = FY[size_t(i) * kk + e], dst[kk + e] = FZ[size_t(i) * kk + e];
-    for (int e = t0; e < kb; e += nt) dst[2 * kk + e] = Fr[size_t(i) * kb + e];
+    if (it < nrows) {
+      const int i = istart - sgn * it;
+      double* dst = ring + (it % 3) * kSlot;
+      for (int e = t0; e < kk; e += nt) {
+        cp_async8(dst + e, FY + size_t(i) * kk + e);
+        cp_async8(dst + kk + e, FZ + size_t(i) * kk + e);
+      }
+      for (int e = t0; e < kb; e += nt) cp_async8(dst + 2 * kk + e, Fr + size_t(i) * kb + e);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per call, also when empty
   };
   auto emit = [&](int i, double out) {
     if (row) {
@@ -564,6 +575,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     if (lane < LD) xs[lane] = dir == 0 ? u0 : u1, xs[LD + lane] = dir == 0 ? u1 : u0;
     emit(dir == 0 ? mid : mid + 1, dir == 0 ? u0 : u1);
   }
+  asm volatile("cp.async.wait_group 1;" ::: "memory");  // row 0 has landed (row 1 may be in flight)
   __syncthreads();
   for (int it = 0; it < nrows; ++it) {
     if (wid == 0) {
@@ -583,11 +595,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       emit(istart - sgn * it, out);
       __syncwarp();
       if (lane < LD) xs[((it & 1) ^ 1) * LD + lane] = out;  // becomes x1 of the next row; the old x1 becomes x2
-    } else {
-      fetch(it + 2, tid - 32, kThreads - 32);
     }
+    fetch(it + 2, tid, kThreads);                          // slot (it + 2) % 3 was consumed in iteration it - 1
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // row it + 1 has landed
     __syncthreads();
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   KT(11)
   KT_PRINT(b, dir)
 }
