@@ -17,7 +17,7 @@
 // body; 12.8 MB for 64 x 40 x 13 bodies, L2 resident): A perturbs E_{t-1}, B perturbs E_t, C (mass-matrix
 // column) needs the pose of E_{t+1}.  The arithmetic per body and the order of every accumulation are
 // those of chain_eval, so the unaffected rows are exactly zero and the affected ones agree with the full
-// evaluation to the last bits.  No shared memory is used: occupancy is bounded by registers only.
+// evaluation to the last bits.  Shared memory holds only the baked tables: occupancy is bounded by registers.
 #include "dynamics_chain.cuh"
 
 namespace idto {
@@ -28,16 +28,14 @@ constexpr int kMaxDown = 4;  // bodies in the owner's subtree chain (checked at 
 constexpr int kMaxUp = 7;    // ancestors of the owner
 constexpr int kMaxRows = kMaxDown + 6 + (kMaxUp - 1);  // affected rows: subtree joints + ancestors' joints
 
-struct GModel {  // the baked tables, read from global memory (L1/L2 resident: ~5 KB)
+struct GModel {  // the baked tables (staged in shared memory by one bulk TMA copy per CTA)
   const int *parent, *jtype, *qs, *vs, *nchild, *child, *flags, *gbody, *gtype, *pA, *pB, *gslot;
   const double *XPF, *RMB, *axis, *mass, *com, *inertia, *damping, *gdims, *XBG, *XWGs;
   int nb, nbp, nq, nv, ng, np;
   V3 g;
 };
-__device__ __forceinline__ GModel make_gmodel(const DevModel& dm) {
+__device__ __forceinline__ GModel make_gmodel(const DevModel& dm, const int* si, const double* sd) {
   GModel M;
-  const int* si = dm.itab;
-  const double* sd = dm.dtab;
   M.parent = si + dm.o_parent, M.jtype = si + dm.o_jtype, M.qs = si + dm.o_qs, M.vs = si + dm.o_vs;
   M.nchild = si + dm.o_nchild, M.child = si + dm.o_child, M.flags = si + dm.o_flags;
   M.gbody = si + dm.o_gbody, M.gtype = si + dm.o_gtype, M.pA = si + dm.o_pA, M.pB = si + dm.o_pB;
@@ -298,6 +296,10 @@ __global__ void __launch_bounds__(128) k_partials_path(DevModel dm, SolverConsts
   const int T = sc.T, nq = sc.nq, nv = sc.nv, np = dm.npath;
   // consecutive threads take consecutive (problem, step) items of the SAME column and phase: a warp runs one
   // code path with one trip count (mixing the phases in a warp serialised three instantiations: 523 us)
+  extern __shared__ __align__(16) unsigned char smem[];
+  int* si = reinterpret_cast<int*>(smem);
+  double* sd = reinterpret_cast<double*>(smem + dm.itab_bytes);
+  stage_model(dm, si, sd, reinterpret_cast<uint64_t*>(smem + dm.itab_bytes + dm.dtab_bytes));
   const long idx = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const long nitem = long(sc.B) * T;
   if (idx >= nitem * 3 * np) return;
@@ -305,10 +307,10 @@ __global__ void __launch_bounds__(128) k_partials_path(DevModel dm, SolverConsts
   const int t = item % T + 1, b = item / T;
   if (!force && !bf.ctl[b].derivs_dirty) return;
   if ((phase == 1 && t >= T) || (phase == 2 && t >= T - 1)) return;
-  const GModel M = make_gmodel(dm);
-  const int i = (dm.itab + dm.o_pathcols)[ci];
+  const GModel M = make_gmodel(dm, si, sd);
+  const int i = (si + dm.o_pathcols)[ci];
   PathPlan pl;
-  pl.owner = (dm.itab + dm.o_qowner)[i];
+  pl.owner = (si + dm.o_qowner)[i];
   pl.ndown = 0;
   for (int k = pl.owner;;) {
     pl.down[pl.ndown++] = k;
@@ -398,11 +400,12 @@ void launch_partials_path(const DevModel& dm, const SolverConsts& sc, const Solv
   if (dm.npath == 0) return;
   const long n = long(sc.B) * sc.T * 3 * dm.npath;
   const int grid = int((n + 127) / 128);
+  const int smem = model_smem_bytes(dm);
   g_launch_counter += 1;
   switch (sc.method) {
-    case IDTO_GRAD_FORWARD: k_partials_path<IDTO_GRAD_FORWARD><<<grid, 128, 0, stream>>>(dm, sc, bf, force ? 1 : 0); break;
-    case IDTO_GRAD_CENTRAL: k_partials_path<IDTO_GRAD_CENTRAL><<<grid, 128, 0, stream>>>(dm, sc, bf, force ? 1 : 0); break;
-    default: k_partials_path<IDTO_GRAD_CENTRAL4><<<grid, 128, 0, stream>>>(dm, sc, bf, force ? 1 : 0); break;
+    case IDTO_GRAD_FORWARD: k_partials_path<IDTO_GRAD_FORWARD><<<grid, 128, smem, stream>>>(dm, sc, bf, force ? 1 : 0); break;
+    case IDTO_GRAD_CENTRAL: k_partials_path<IDTO_GRAD_CENTRAL><<<grid, 128, smem, stream>>>(dm, sc, bf, force ? 1 : 0); break;
+    default: k_partials_path<IDTO_GRAD_CENTRAL4><<<grid, 128, smem, stream>>>(dm, sc, bf, force ? 1 : 0); break;
   }
 }
 

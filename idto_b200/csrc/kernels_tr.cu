@@ -12,50 +12,48 @@ constexpr int kRowThreads = 128;
 
 // Block row i of y = H~ x for the symmetric block penta-diagonal matrix given by its lower bands
 // (PentaDiagonalMatrix::MultiplyBy, penta_diagonal_matrix.cc:181-207; D_i = B_{i+1}^T, E_i = A_{i+2}^T).
-// xs[5][k] holds the blocks i-2..i+2 of x (zeros outside the matrix); thread-task (term, row) computes one
-// k-long dot product into terms[5][k]; the caller sums the five terms in the reference's order.
-__device__ __forceinline__ void block_row_matvec(const SolverConsts& sc, const double* SA, const double* SB,
-                                                 const double* SC, int i, const double* xs, double* terms, int tid,
-                                                 int nt) {
+// The five blocks of the row are first staged in shared memory `hs` [5][k*k] by all threads (independent,
+// coalesced loads: one L2 round trip instead of one per multiply-add chain step); xs[5][k] holds the blocks
+// i-2..i+2 of x (zeros outside the matrix); thread-task (term, row) computes one k-long dot product into
+// terms[5][k]; the caller sums the five terms in the reference's order.
+__device__ __forceinline__ void stage_row_blocks(const SolverConsts& sc, const double* SA, const double* SB,
+                                                 const double* SC, int i, double* hs, int tid, int nt) {
   const int k = sc.nq, kk = k * k, nblk = sc.T + 1;
+  const double* src[5] = {SC + size_t(i) * kk, i >= 1 ? SB + size_t(i) * kk : nullptr,
+                          i >= 2 ? SA + size_t(i) * kk : nullptr, i < nblk - 1 ? SB + size_t(i + 1) * kk : nullptr,
+                          i < nblk - 2 ? SA + size_t(i + 2) * kk : nullptr};
+#pragma unroll
+  for (int term = 0; term < 5; ++term) {
+    const double* p = src[term];
+#pragma unroll 4
+    for (int e = tid; e < kk; e += nt) hs[term * kk + e] = p ? p[e] : 0.0;
+  }
+}
+__device__ __forceinline__ void block_row_matvec(const SolverConsts& sc, const double* hs, const double* xs,
+                                                 double* terms, int tid, int nt) {
+  const int k = sc.nq, kk = k * k;
   for (int task = tid; task < 5 * k; task += nt) {
     const int term = task / k, r = task - term * k;
+    const double* Hb = hs + term * kk;
+    // terms 0..4 multiply x_i, x_{i-1}, x_{i-2}, x_{i+1}, x_{i+2}; the last two use the transposed block
+    const double* x = xs + (term == 0 ? 2 : (term == 1 ? 1 : (term == 2 ? 0 : (term == 3 ? 3 : 4)))) * k;
     double acc = 0.0;
-    if (term == 0) {
-      const double* C = SC + size_t(i) * kk;
-      const double* x = xs + 2 * k;
-#pragma unroll 8
-      for (int c = 0; c < k; ++c) acc += C[c * k + r] * x[c];
-    } else if (term == 1) {
-      if (i >= 1) {
-        const double* Bm = SB + size_t(i) * kk;
-        const double* x = xs + k;
-#pragma unroll 8
-        for (int c = 0; c < k; ++c) acc += Bm[c * k + r] * x[c];
-      }
-    } else if (term == 2) {
-      if (i >= 2) {
-        const double* Am = SA + size_t(i) * kk;
-#pragma unroll 8
-        for (int c = 0; c < k; ++c) acc += Am[c * k + r] * xs[c];
-      }
-    } else if (term == 3) {
-      if (i < nblk - 1) {
-        const double* Bn = SB + size_t(i + 1) * kk;  // D_i(r,c) = B_{i+1}(c,r)
-        const double* x = xs + 3 * k;
-#pragma unroll 8
-        for (int c = 0; c < k; ++c) acc += Bn[r * k + c] * x[c];
-      }
+    if (term < 3) {
+      for (int c = 0; c < k; ++c) acc += Hb[c * k + r] * x[c];
     } else {
-      if (i < nblk - 2) {
-        const double* An = SA + size_t(i + 2) * kk;
-        const double* x = xs + 4 * k;
-#pragma unroll 8
-        for (int c = 0; c < k; ++c) acc += An[r * k + c] * x[c];
-      }
+      for (int c = 0; c < k; ++c) acc += Hb[r * k + c] * x[c];
     }
     terms[task] = acc;
   }
+}
+
+// Sum of the per-block-row partials part[j][q], j < nblk, by warp 0 (all 32 lanes call): lane j takes rows
+// j, j+32, ... (independent L2 loads), then a fixed shuffle tree — deterministic, and one L2 round trip
+// instead of nblk dependent ones (the serial sum was a 12 us tail on every launch).
+__device__ __forceinline__ double partials_sum(const double* part, int nblk, int q, int lane) {
+  double x = 0.0;
+  for (int j = lane; j < nblk; j += 32) x += __ldcg(part + 4 * j + q);
+  return warp_sum(x);
 }
 
 // Deterministic sum over the first k <= 32 lanes of warp 0 (fixed shuffle tree).
@@ -84,6 +82,7 @@ __device__ __forceinline__ bool last_block_of_problem(int* cnt, int nblk) {
 // SMs.  Every CTA rebuilds the five blocks of gm its row touches (a few hundred multiply-adds), writes
 // its own block of gm and its partial sums; the last CTA of a problem adds them up in block order.
 __global__ void __launch_bounds__(kRowThreads) k_gm_matvec(SolverConsts sc, SolverBufs bf, int force) {
+  extern __shared__ __align__(16) double dyn[];
   __shared__ double xs[5 * 32], terms[5 * 32];
   const int nblk = sc.T + 1, b = blockIdx.x / nblk, i = blockIdx.x % nblk;
   if (!force && !bf.ctl[b].derivs_dirty) return;
@@ -92,6 +91,8 @@ __global__ void __launch_bounds__(kRowThreads) k_gm_matvec(SolverConsts sc, Solv
   const double* gs = bf.gs + size_t(b) * n;
   const double* lam = bf.lambda + size_t(b) * nh;
   const bool eq = sc.eq && nh > 0;
+  double* hs = dyn;  // [5][k*k] blocks of the row
+  stage_row_blocks(sc, bf.SA + hb, bf.SB + hb, bf.SC + hb, i, hs, tid, nt);
   for (int e = tid; e < 5 * k; e += nt) {
     const int s = i - 2 + e / k, c = e % k;
     double val = 0.0;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kRowThreads) k_gm_matvec(SolverConsts sc, Solv
     xs[e] = val;
   }
   __syncthreads();
-  block_row_matvec(sc, bf.SA + hb, bf.SB + hb, bf.SC + hb, i, xs, terms, tid, nt);
+  block_row_matvec(sc, hs, xs, terms, tid, nt);
   __syncthreads();
   if (tid < 32) {
     double gHg = 0.0, gg = 0.0, hl = 0.0;
@@ -130,12 +131,14 @@ __global__ void __launch_bounds__(kRowThreads) k_gm_matvec(SolverConsts sc, Solv
       pp[0] = gHg, pp[1] = gg, pp[2] = hl;
     }
   }
-  if (last_block_of_problem(bf.cnt + b, nblk) && tid == 0) {
+  if (last_block_of_problem(bf.cnt + b, nblk) && tid < 32) {
     const double* pp = bf.part + size_t(b) * nblk * 4;
-    double gHg = 0.0, gg = 0.0, hl = 0.0;
-    for (int j = 0; j < nblk; ++j) gHg += __ldcg(pp + 4 * j), gg += __ldcg(pp + 4 * j + 1), hl += __ldcg(pp + 4 * j + 2);
-    bf.red[b * 8 + 0] = gHg, bf.red[b * 8 + 1] = gg;
-    bf.merit[b] = eq ? bf.st.cost[b] + hl : bf.st.cost[b];
+    const double gHg = partials_sum(pp, nblk, 0, tid), gg = partials_sum(pp, nblk, 1, tid);
+    const double hl = partials_sum(pp, nblk, 2, tid);
+    if (tid == 0) {
+      bf.red[b * 8 + 0] = gHg, bf.red[b * 8 + 1] = gg;
+      bf.merit[b] = eq ? bf.st.cost[b] + hl : bf.st.cost[b];
+    }
   }
 }
 
@@ -237,12 +240,14 @@ __global__ void __launch_bounds__(kRowThreads) k_trust_update(SolverConsts sc, S
   const size_t hb = size_t(b) * nblk * k * k;
   const double* dqs = bf.tmp1 + size_t(b) * n;
   const double* gm = bf.gm + size_t(b) * n;
+  extern __shared__ __align__(16) double dyn[];
+  stage_row_blocks(sc, bf.SA + hb, bf.SB + hb, bf.SC + hb, i, dyn, tid, nt);
   for (int e = tid; e < 5 * k; e += nt) {
     const int s = i - 2 + e / k;
     xs[e] = (s >= 0 && s < nblk) ? dqs[s * k + e % k] : 0.0;
   }
   __syncthreads();
-  block_row_matvec(sc, bf.SA + hb, bf.SB + hb, bf.SC + hb, i, xs, terms, tid, nt);
+  block_row_matvec(sc, dyn, xs, terms, tid, nt);
   __syncthreads();
   if (tid < 32) {
     double ht = 0.0, gt = 0.0, hl = 0.0, h2 = 0.0;
@@ -263,13 +268,15 @@ __global__ void __launch_bounds__(kRowThreads) k_trust_update(SolverConsts sc, S
     }
   }
   if (!last_block_of_problem(bf.cnt + b, nblk)) return;
-  double ht = 0.0, gt = 0.0, hl = 0.0, h2 = 0.0;
-  {
+  if (tid < 32) {
     const double* pp = bf.part + size_t(b) * nblk * 4;
-    for (int j = 0; j < nblk; ++j)
-      ht += __ldcg(pp + 4 * j), gt += __ldcg(pp + 4 * j + 1), hl += __ldcg(pp + 4 * j + 2), h2 += __ldcg(pp + 4 * j + 3);
+    for (int qq = 0; qq < 4; ++qq) {
+      const double x = partials_sum(pp, nblk, qq, tid);
+      if (tid == 0) red[qq] = x;
+    }
   }
-  (void)red;
+  __syncthreads();
+  const double ht = red[0], gt = red[1], hl = red[2], h2 = red[3];
   const double merit_k = bf.merit[b];
   const double merit_kp = bf.sc.cost[b] + hl;
   const double predicted = -gt - 0.5 * ht;
@@ -378,7 +385,14 @@ void launch_clear_dirty(const SolverConsts& sc, const SolverBufs& bf, cudaStream
 
 void launch_gm_matvec(const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
   g_launch_counter += 1;
-  k_gm_matvec<<<sc.B*(sc.T + 1), kRowThreads, 0, stream>>>(sc, bf, force ? 1 : 0);
+  const int smem = 5 * sc.nq * sc.nq * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_gm_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_trust_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  k_gm_matvec<<<sc.B*(sc.T + 1), kRowThreads, smem, stream>>>(sc, bf, force ? 1 : 0);
 }
 
 void launch_dogleg(const SolverConsts& sc, const SolverBufs& bf, cudaStream_t stream) {
@@ -390,7 +404,12 @@ void launch_trust_update(const DevModel& dm, const SolverConsts& sc, const Solve
                          cudaStream_t stream) {
   (void)dm;
   g_launch_counter += 1;
-  k_trust_update<<<sc.B*(sc.T + 1), kRowThreads, 0, stream>>>(sc, bf, commit ? 1 : 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_trust_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  k_trust_update<<<sc.B*(sc.T + 1), kRowThreads, 5 * sc.nq * sc.nq * 8, stream>>>(sc, bf, commit ? 1 : 0);
 }
 
 }  // namespace idto

@@ -237,3 +237,30 @@ def test_substreams_do_not_change_results(oracle_mod):
         out[ns] = (it.copy(), stats.copy(), q.copy(), tau.copy(), gs.get("delta").copy())
     for a, b in zip(out[1], out[4]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["mini_cheetah", "hopper", "spinner"])
+@pytest.mark.parametrize("method", [GRAD_FORWARD, GRAD_CENTRAL, GRAD_CENTRAL4])
+def test_path_columns_match_full_evaluations(name, method, monkeypatch):
+    """The single-lane subtree evaluations (kernels_path.cu) against full evaluations of the same columns
+    (IDTO_PATH_COLS=0): same arithmetic per body, so almost every entry is bit-identical and the rest differ
+    by last-bit effects amplified by 1/dq."""
+    from idto_b200 import capi
+    m, dt, prob, params, guess = getattr(problems, name)(gradients_method=method)
+    rng = np.random.default_rng(3)
+    q = np.array(guess, float)[None].repeat(2, 0)
+    q[:, 1:] += rng.normal(0, 0.03, q[:, 1:].shape)
+    out = {}
+    for tag, env in (("full", "0"), ("path", "1")):
+        monkeypatch.setenv("IDTO_PATH_COLS", env)
+        gs = capi.BatchSolver(capi.Model(m), dt, prob, params, 2)
+        gs.set_q(q)
+        gs.eval(1)
+        out[tag] = {f: gs.get(f) for f in ("dtau_dqm", "dtau_dqt", "dtau_dqp")}
+    for f in ("dtau_dqm", "dtau_dqt", "dtau_dqp"):
+        a, b = out["full"][f], out["path"][f]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f
+        mask = ~np.isnan(a)
+        scale = max(1.0, np.max(np.abs(a[mask])))
+        assert np.max(np.abs(a[mask] - b[mask])) < 1e-9 * scale, f
+        assert np.mean(a[mask] == b[mask]) > 0.99, f
