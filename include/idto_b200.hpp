@@ -255,6 +255,18 @@ class WarmStart {
       for (int i = 0; i < cols; ++i) out[t][i] = buf[size_t(t) * cols + i];
     return out;
   }
+  // The MPC shell between two re-solves (ModelPredictiveController::UpdateAbstractState,
+  // examples/mpc_controller.cc:43-98), on the device: the stored solution is spline-shifted by `elapsed`
+  // seconds into the new guess, q_nom moves with q0 for the selected coordinates, (q0, v0) become the initial
+  // conditions.  `q_nom_relative_to_q_init` may be empty (no shift).
+  void AdvanceFromMeasuredState(double elapsed, const VectorXd& q0, const VectorXd& v0,
+                                const std::vector<bool>& q_nom_relative_to_q_init = {}) {
+    std::vector<double> sel(q_nom_relative_to_q_init.begin(), q_nom_relative_to_q_init.end());
+    if (q0.size() != nq_ || (!sel.empty() && int(sel.size()) != nq_))
+      throw std::runtime_error("AdvanceFromMeasuredState: wrong sizes");
+    ThrowOnError(idto_mpc_advance(s_, &elapsed, q0.data(), v0.data(), sel.empty() ? nullptr : sel.data()),
+                 "idto_mpc_advance");
+  }
   idto_solver_t handle() const { return s_; }
   int version{0};
 

@@ -88,6 +88,15 @@ int main(int argc, char** argv) {
     threw = true;  // stats must be empty (cc:2225)
   }
   CHECK(threw);
+
+  // MPC shell on the device (examples/mpc_controller.cc:43-98): with zero elapsed time the shifted guess is
+  // the stored solution at its knots, with q_0 replaced by the measured state
+  const std::vector<VectorXd> before = ws->get_q();
+  ws->AdvanceFromMeasuredState(0.0, VectorXd{0.32, 1.48, 0.02}, VectorXd{0.0, 0.0, 0.0}, {false, false, true});
+  const std::vector<VectorXd> after = ws->get_q();
+  CHECK(after[0][0] == 0.32 && after[0][2] == 0.02);
+  for (int t = 1; t <= 40; ++t)
+    for (int i = 0; i < 3; ++i) CHECK(std::fabs(after[t][i] - before[t][i]) < 1e-12);
   std::printf("C++ API test OK\n");
   return 0;
 }
