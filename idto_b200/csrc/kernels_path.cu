@@ -290,7 +290,7 @@ __device__ __forceinline__ void path_eval(const GModel& M, const SolverConsts& s
 
 }  // namespace
 
-// One thread per (phase A/B/C, path column, problem, step t = 1..T).
+// One thread per (phase A/B/C, path column, problem, step t = 1..T, stencil point).
 template <int METHOD>
 __global__ void __launch_bounds__(128) k_partials_path(DevModel dm, SolverConsts sc, SolverBufs bf, int force) {
   const int T = sc.T, nq = sc.nq, nv = sc.nv, np = dm.npath;
@@ -300,13 +300,19 @@ __global__ void __launch_bounds__(128) k_partials_path(DevModel dm, SolverConsts
   int* si = reinterpret_cast<int*>(smem);
   double* sd = reinterpret_cast<double*>(smem + dm.itab_bytes);
   stage_model(dm, si, sd, reinterpret_cast<uint64_t*>(smem + dm.itab_bytes + dm.dtab_bytes));
+  // NK adjacent lanes share one (phase, column, item) and evaluate one stencil point each (+dq, -dq, +2dq, -2dq):
+  // twice / four times the warps for the same registers per thread, which is what hides the L2 latency of the
+  // records; the stencil is combined with shuffles.  The mass-matrix phase C has a single evaluation (lane 0).
+  constexpr int NK = METHOD == IDTO_GRAD_CENTRAL4 ? 4 : (METHOD == IDTO_GRAD_CENTRAL ? 2 : 1);
   const long idx = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const long nitem = long(sc.B) * T;
-  if (idx >= nitem * 3 * np) return;
-  const int item = int(idx % nitem), ci = int((idx / nitem) % np), phase = int(idx / (nitem * np));
+  if (idx >= nitem * 3 * np * NK) return;
+  const int kk = int(idx % NK);
+  const long gidx = idx / NK;
+  const int item = int(gidx % nitem), ci = int((gidx / nitem) % np), phase = int(gidx / (nitem * np));
   const int t = item % T + 1, b = item / T;
   if (!force && !bf.ctl[b].derivs_dirty) return;
-  if ((phase == 1 && t >= T) || (phase == 2 && t >= T - 1)) return;
+  if ((phase == 1 && t >= T) || (phase == 2 && (t >= T - 1 || kk > 0))) return;
   const GModel M = make_gmodel(dm, si, sd);
   const int i = (si + dm.o_pathcols)[ci];
   PathPlan pl;
@@ -336,32 +342,20 @@ __global__ void __launch_bounds__(128) k_partials_path(DevModel dm, SolverConsts
   Perturb pt;
   pt.owner = pl.owner, pt.local = 0, pt.sl = 0, pt.quatcol = false;
   pt.nv3 = pt.na3 = {0, 0, 0};
-  constexpr int NK = METHOD == IDTO_GRAD_CENTRAL4 ? 4 : (METHOD == IDTO_GRAD_CENTRAL ? 2 : 1);
-  double R0[kMaxRows], R1[kMaxRows], R2[kMaxRows];
+  double R0[kMaxRows], R1[kMaxRows], R2[kMaxRows], R3[kMaxRows];
+  for (int r = 0; r < kMaxRows; ++r) R0[r] = 0.0;
   double* dst;
   const double* tau_base;
+  const double m = ((kk & 1) ? -1.0 : 1.0) * ((kk >= 2) ? 2.0 : 1.0);  // this lane's stencil point
   if (phase == 0) {  // A: tau[t-1] = ID(q_t^e, v_t^e, a_{t-1}^e)   (cc:526-531, 763-787)
-#pragma unroll 1
-    for (int kk = 0; kk < NK; ++kk) {
-      const double m = ((kk & 1) ? -1.0 : 1.0) * ((kk >= 2) ? 2.0 : 1.0);
-      pt.dq = m * dq, pt.cv = m * dv, pt.ca = m * da, pt.uv = 1.0, pt.ua = 1.0;
-      path_eval<kEvalFull>(M, sc, pl, rec_of(t - 1), qB + size_t(t) * nq, vB + size_t(t) * nv, aB + size_t(t - 1) * nv, pt,
-                           (kk & 1) ? R1 : R0);
-      if (METHOD == IDTO_GRAD_CENTRAL4 && kk == 1)
-        for (int r = 0; r < kMaxRows; ++r) R2[r] = R0[r] - R1[r];
-    }
+    pt.dq = m * dq, pt.cv = m * dv, pt.ca = m * da, pt.uv = 1.0, pt.ua = 1.0;
+    path_eval<kEvalFull>(M, sc, pl, rec_of(t - 1), qB + size_t(t) * nq, vB + size_t(t) * nv, aB + size_t(t - 1) * nv, pt, R0);
     dst = bf.dqp + (size_t(b) * T + (t - 1)) * nv * nq;
     tau_base = bf.st.tau + (size_t(b) * T + (t - 1)) * nv;
   } else if (phase == 1) {  // B: tau[t] = ID(q_{t+1}, v_{t+1}^e, a_t^e)   (cc:533-540, 788-814)
-#pragma unroll 1
-    for (int kk = 0; kk < NK; ++kk) {
-      const double m = ((kk & 1) ? -1.0 : 1.0) * ((kk >= 2) ? 2.0 : 1.0);
-      pt.dq = 0.0, pt.cv = -(m * dv), pt.ca = -(m * da), pt.uv = 1.0, pt.ua = 1.0 + 1.0;
-      path_eval<kEvalSharedPose>(M, sc, pl, rec_of(t), qB + size_t(t + 1) * nq, vB + size_t(t + 1) * nv, aB + size_t(t) * nv,
-                                 pt, (kk & 1) ? R1 : R0);
-      if (METHOD == IDTO_GRAD_CENTRAL4 && kk == 1)
-        for (int r = 0; r < kMaxRows; ++r) R2[r] = R0[r] - R1[r];
-    }
+    pt.dq = 0.0, pt.cv = -(m * dv), pt.ca = -(m * da), pt.uv = 1.0, pt.ua = 1.0 + 1.0;
+    path_eval<kEvalSharedPose>(M, sc, pl, rec_of(t), qB + size_t(t + 1) * nq, vB + size_t(t + 1) * nv, aB + size_t(t) * nv,
+                               pt, R0);
     dst = bf.dqt + (size_t(b) * T + t) * nv * nq;
     tau_base = bf.st.tau + (size_t(b) * T + t) * nv;
   } else {  // C: dtau_dqm[t+1] = M(q_{t+2}) N+_{t+1} / dt^2   (cc:552-561)
@@ -369,6 +363,15 @@ __global__ void __launch_bounds__(128) k_partials_path(DevModel dm, SolverConsts
     path_eval<kEvalSharedPoseNoBias>(M, sc, pl, rec_of(t + 1), qB + size_t(t + 2) * nq, nullptr, nullptr, pt, R0);
     dst = bf.dqm + (size_t(b) * T + (t + 1)) * nv * nq;
     tau_base = nullptr;
+  }
+  if (NK > 1 && phase < 2) {  // the other stencil points sit in the next NK-1 lanes (same warp: NK divides 32)
+    const unsigned mask = __activemask();
+#pragma unroll
+    for (int r = 0; r < kMaxRows; ++r) {
+      R1[r] = __shfl_down_sync(mask, R0[r], 1);
+      if (NK > 2) R2[r] = __shfl_down_sync(mask, R0[r], 2), R3[r] = __shfl_down_sync(mask, R0[r], 3);
+    }
+    if (kk > 0) return;
   }
   // column i of the block: zero except for the affected rows
   double* col = dst + size_t(i) * nv;
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(128) k_partials_path(DevModel dm, SolverConsts
     else if (METHOD == IDTO_GRAD_CENTRAL)
       val = 0.5 * (R0[nr] - R1[nr]) / dq;  // cc:785
     else
-      val = 2.0 / 3.0 * R2[nr] / dq - 1.0 / 12.0 * (R0[nr] - R1[nr]) / dq;  // cc:782-783
+      val = 2.0 / 3.0 * (R0[nr] - R1[nr]) / dq - 1.0 / 12.0 * (R2[nr] - R3[nr]) / dq;  // cc:782-783
     col[row] = val;
     ++nr;
   };
@@ -398,7 +401,8 @@ __global__ void __launch_bounds__(128) k_partials_path(DevModel dm, SolverConsts
 void launch_partials_path(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
                           cudaStream_t stream) {
   if (dm.npath == 0) return;
-  const long n = long(sc.B) * sc.T * 3 * dm.npath;
+  const int nk = sc.method == IDTO_GRAD_CENTRAL4 ? 4 : (sc.method == IDTO_GRAD_CENTRAL ? 2 : 1);
+  const long n = long(sc.B) * sc.T * 3 * dm.npath * nk;
   const int grid = int((n + 127) / 128);
   const int smem = model_smem_bytes(dm);
   g_launch_counter += 1;
