@@ -176,9 +176,13 @@ class BatchSolver:
     def mpc_advance(self, elapsed, q0, v0, q_nom_selector=None):
         """Device-side MPC shell between two re-solves (examples/mpc_controller.cc:43-98): spline-shifted
         guess, shifted nominal trajectory, new initial conditions.  elapsed: scalar or [batch] seconds."""
-        el = np.ascontiguousarray(np.broadcast_to(np.asarray(elapsed, float), (self.B,)))
-        q0 = self._arr(q0, (self.B, self.nq))
-        v0 = self._arr(v0, (self.B, self.nv))
+        def ready(x, shape):  # fast path of the MPC loop: the caller's (pinned) float64 arrays go through untouched
+            return isinstance(x, np.ndarray) and x.dtype == np.float64 and x.shape == shape and x.flags.c_contiguous
+
+        el = elapsed if ready(elapsed, (self.B,)) else np.ascontiguousarray(
+            np.broadcast_to(np.asarray(elapsed, float), (self.B,)))
+        q0 = q0 if ready(q0, (self.B, self.nq)) else self._arr(q0, (self.B, self.nq))
+        v0 = v0 if ready(v0, (self.B, self.nv)) else self._arr(v0, (self.B, self.nv))
         sel = None if q_nom_selector is None else np.ascontiguousarray(np.asarray(q_nom_selector, float).reshape(self.nq))
         _check(lib().idto_mpc_advance(self.h, _p(el), _p(q0), _p(v0), None if sel is None else _p(sel)))
 

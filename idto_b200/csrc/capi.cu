@@ -76,6 +76,7 @@ struct idto_solver_s {
   bool profile = false;
   std::map<std::string, std::vector<ProfEvent>> prof;
   std::vector<ProbCtl> ctl_host;
+  int* status_host = nullptr;  // pinned mirror of bf.status: the D2H of idto_synchronize stays asynchronous
   size_t stats_cap = 0;
   // sub-batches on their own streams: the latency-bound per-problem kernels (KKT sweep, TR scalars)
   // of one sub-batch overlap with the throughput-bound kernels (ID partials, assembly) of another
@@ -314,9 +315,10 @@ int ensure_stats(idto_solver_s* s, size_t cap) {
 
 int check_status(idto_solver_s* s) {
   use_main(s);
-  int st = 0;
-  IDTO_CUDA_CHECK(cudaMemcpyAsync(&st, s->bf.status, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  if (!s->status_host) IDTO_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&s->status_host), sizeof(int), cudaHostAllocDefault));
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(s->status_host, s->bf.status, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   IDTO_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+  const int st = *s->status_host;
   if (st != 0) {
     set_last_error("penta-diagonal factorisation failed (singular diagonal block)");
     int zero = 0;
@@ -704,6 +706,7 @@ int idto_solver_destroy(idto_solver_t s) {
   for (auto st : s->sub_streams) cudaStreamDestroy(st);
   for (auto ev : s->sub_done) cudaEventDestroy(ev);
   if (s->ev_start) cudaEventDestroy(s->ev_start);
+  if (s->status_host) cudaFreeHost(s->status_host);
   for (auto& kv : s->prof)
     for (auto& e : kv.second) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
   s->mem.release();

@@ -354,39 +354,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const double* Yp = Yb + prv * kl;
       const double* Zp = Zb + prv * kl;
       const double* rp = rb + prv * LD;
-      double kr[KB];
+      // out = K_i [Y_{n-1} | Z_{n-1} | r_{n-1}]  (kb x (2 kb + 1)) on the fp64 tensor cores: DMMA m8n8k4 tiles,
+      // one 8-column tile of the right-hand side per warp, the K fragments of all (row tile, k tile) pairs in
+      // registers.  The scalar version was bound by the shared-memory pipe (one broadcast load per multiply-add
+      // column step: 2.7k cycles per block row); fragments are full-width loads.
+      constexpr int NW = kThreads / 32;
+      constexpr int MT = (KB + 7) / 8, KT4 = (KB + 3) / 4, NTN = (2 * KB + 1 + 7) / 8;
+      const int grp = lane >> 2, tig = lane & 3;
+      double afr[MT][KT4];
 #pragma unroll
-      for (int j = 0; j < KB; ++j) kr[j] = Kb[j * LD + r];
-      // 2*kb + 1 columns (G, Yrhs, r) over all warps; every warp runs its columns as independent chains
-      constexpr int NW = kThreads / 32, NTA = (2 * KB + 1 + NW - 1) / NW;
-      double acc[NTA];
-      const double* srcs[NTA];
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int k = 0; k < NTA; ++k) {
-        const int t = wid + NW * k, c = t < kb ? t : t - kb;
-        acc[k] = 0.0;
-        srcs[k] = t < kb ? Yp + c * LD : (t < 2 * kb ? Zp + c * LD : rp);
-      }
-#pragma unroll
-      for (int j = 0; j < KB; j += 2) {
-#pragma unroll
-        for (int k = 0; k < NTA; ++k) {
-          const double2 v = *reinterpret_cast<const double2*>(srcs[k] + j);
-          acc[k] = fma(kr[j], v.x, acc[k]);
-          if (j + 1 < KB) acc[k] = fma(kr[j + 1], v.y, acc[k]);
+        for (int kt = 0; kt < KT4; ++kt) {
+          const int rr = mt * 8 + grp, kc = kt * 4 + tig;
+          afr[mt][kt] = (rr < kb && kc < kb) ? Kb[kc * LD + rr] : 0.0;
         }
-      }
+      for (int nt = wid; nt < NTN; nt += NW) {
+        double c0[MT], c1[MT];
 #pragma unroll
-      for (int k = 0; k < NTA; ++k) {
-        const int t = wid + NW * k, c = t < kb ? t : t - kb;
-        if (row) {
-          if (t < kb) {
-            Mg[cur * kl + c * LD + r] -= acc[k];
-          } else if (t < 2 * kb) {
-            My[c * LD + r] = rw[3 * kl + c * LD + r] - acc[k];
-            Mz[c * LD + r] = rw[4 * kl + c * LD + r];
-          } else if (t == 2 * kb) {
-            rv[cur * LD + r] -= acc[k];
+        for (int mt = 0; mt < MT; ++mt) c0[mt] = 0.0, c1[mt] = 0.0;
+        const int nb = nt * 8 + grp;  // column of the flat right-hand side this lane feeds
+        const double* bsrc = nb < kb ? Yp + nb * LD : (nb < 2 * kb ? Zp + (nb - kb) * LD : rp);
+#pragma unroll
+        for (int kt = 0; kt < KT4; ++kt) {
+          const int kr = kt * 4 + tig;
+          const double bfr = (kr < kb && nb <= 2 * kb) ? bsrc[kr] : 0.0;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0[mt]), "+d"(c1[mt])
+                         : "d"(afr[mt][kt]), "d"(bfr));
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int rr = mt * 8 + grp;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int t = nt * 8 + 2 * tig + h;
+            const double acc = h ? c1[mt] : c0[mt];
+            if (rr < kb) {
+              if (t < kb) {
+                Mg[cur * kl + t * LD + rr] -= acc;
+              } else if (t < 2 * kb) {
+                const int c = t - kb;
+                My[c * LD + rr] = rw[3 * kl + c * LD + rr] - acc;
+                Mz[c * LD + rr] = rw[4 * kl + c * LD + rr];
+              } else if (t == 2 * kb) {
+                rv[cur * LD + rr] -= acc;
+              }
+            }
           }
         }
       }
