@@ -113,8 +113,8 @@ class Model:
         return out[:self.nu].tolist()
 
     def __del__(self):
-        if getattr(self, "h", None) and self.h.value:
-            lib().idto_model_destroy(self.h)
+        if getattr(self, "h", None) and self.h.value and _LIB is not None and ctypes is not None:
+            _LIB.idto_model_destroy(self.h)
             self.h = ctypes.c_void_p()
 
 
@@ -133,8 +133,8 @@ class BatchSolver:
         _check(lib().idto_solver_create(model.h, ctypes.byref(pd), ctypes.byref(pc), self.B, ctypes.byref(self.h)))
 
     def __del__(self):
-        if getattr(self, "h", None) and self.h.value:
-            lib().idto_solver_destroy(self.h)
+        if getattr(self, "h", None) and self.h.value and _LIB is not None and ctypes is not None:
+            _LIB.idto_solver_destroy(self.h)  # (module globals may already be gone at interpreter shutdown)
             self.h = ctypes.c_void_p()
 
     def _arr(self, x, shape):

@@ -23,11 +23,11 @@ __global__ void __launch_bounds__(64) k_mpc_advance(SolverConsts sc, SolverBufs 
                                                     double* q_nom) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = sc.nq, nv = sc.nv, N = sc.T;  // knots 0..N
-  if (idx >= sc.B * nq) return;
-  const int b = idx / nq, i = idx % nq;
+  const bool live = idx < sc.B * nq;  // (no early return: the CTA shares the spline coefficients below)
+  const int b = live ? idx / nq : 0, i = live ? idx % nq : 0;
   const double h = sc.dt;
   double* q = bf.st.q + size_t(b) * (N + 1) * nq + i;
-  double y[kMaxKnots], M[kMaxKnots], cp[kMaxKnots];
+  double y[kMaxKnots], M[kMaxKnots];
   for (int j = 0; j <= N; ++j) y[j] = q[size_t(j) * nq];
   // second derivatives M_j of the not-a-knot spline on uniform knots:
   //   M_{j-1} + 4 M_j + M_{j+1} = 6 (y_{j+1} - 2 y_j + y_{j-1}) / h^2,  j = 1..N-1
@@ -40,13 +40,16 @@ __global__ void __launch_bounds__(64) k_mpc_advance(SolverConsts sc, SolverBufs 
     // (cp: modified super-diagonal, M doubles as the modified right-hand side)
     auto d = [&](int j) { return rhs(j) - (j == 2 ? M[1] : 0.0) - (j == N - 2 ? M[N - 1] : 0.0); };
     const double mN1 = M[N - 1];
-    cp[2] = 0.25;
-    M[2] = d(2) * 0.25;
-    for (int j = 3; j <= N - 2; ++j) {
-      const double denom = 4.0 - cp[j - 1];
-      cp[j] = 1.0 / denom;
-      M[j] = (d(j) - M[j - 1]) / denom;
+    // the modified super-diagonal cp[j] = 1 / (4 - cp[j-1]) depends on j only: one chain of N dependent
+    // divisions (fp64 division: ~400 cycles) per CTA instead of per thread
+    __shared__ double cp[kMaxKnots];
+    if (threadIdx.x == 0) {
+      cp[2] = 0.25;
+      for (int j = 3; j <= N - 2; ++j) cp[j] = 1.0 / (4.0 - cp[j - 1]);
     }
+    __syncthreads();
+    M[2] = d(2) * 0.25;
+    for (int j = 3; j <= N - 2; ++j) M[j] = (d(j) - M[j - 1]) * cp[j];
     M[N - 1] = mN1;
     for (int j = N - 3; j >= 2; --j) M[j] -= cp[j] * M[j + 1];
     M[0] = 2.0 * M[1] - M[2];
@@ -61,6 +64,7 @@ __global__ void __launch_bounds__(64) k_mpc_advance(SolverConsts sc, SolverBufs 
   } else {  // two points: line
     M[0] = M[1] = 0.0;
   }
+  if (!live) return;
   const double tau0 = elapsed[b], tend = N * h;
   for (int j = 1; j <= N; ++j) {
     double tq = tau0 + j * h;

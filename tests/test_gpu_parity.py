@@ -264,3 +264,41 @@ def test_path_columns_match_full_evaluations(name, method, monkeypatch):
         scale = max(1.0, np.max(np.abs(a[mask])))
         assert np.max(np.abs(a[mask] - b[mask])) < 1e-9 * scale, f
         assert np.mean(a[mask] == b[mask]) > 0.99, f
+
+
+@pytest.mark.parametrize("name,T,eq,batch", [
+    ("hopper", 7, True, 1),        # fewer than 8 block rows: single top-down KKT sweep
+    ("hopper", 8, True, 3),        # shortest two-sided sweep (9 block rows)
+    ("hopper", 9, False, 2),       # no equality constraints: block size nq
+    ("spinner", 13, True, 2),      # odd horizon, every column a path column
+    ("acrobot", 12, True, 1),
+    ("mini_cheetah", 9, True, 33),  # batch that does not divide by the sub-batch streams
+    ("mini_cheetah", 12, False, 2),
+])
+def test_short_horizons_and_block_sizes(oracle_mod, name, T, eq, batch):
+    """Edge cases of the horizon (boundary rows of the three partial bands, the KKT sweep variants) and of the
+    KKT block size, two trust-region iterations against the oracle."""
+    from idto_b200 import capi
+    m, dt, prob, params, guess = getattr(problems, name)(T=T, gradients_method=GRAD_CENTRAL)
+    params.equality_constraints = eq
+    params.max_iterations = 2
+    gs = capi.BatchSolver(capi.Model(m), dt, prob, params, batch)
+    oc = oracle_mod.Oracle(m, dt, prob, params)
+    q = wiggle(guess, 11, 0.02)
+    gs.set_q(q)
+    oc.set_q(q)
+    gs.eval(1)
+    oc.eval(1)
+    sc = max(1.0, np.nanmax(np.abs(oc.get("dtau_dqp"))))
+    for f in ("dtau_dqm", "dtau_dqt", "dtau_dqp"):
+        for b in (0, batch - 1):
+            assert relerr(gs.get(f)[b], oc.get(f), sc) < 2e-6, (f, b)
+    it, _, stats = gs.solve(2)
+    k, _, so = oc.solve(2)
+    assert it[0] == k == 2 and it[batch - 1] == 2
+    for b in (0, batch - 1):
+        assert np.array_equal(stats[b, :, 1], so[:, 1])  # same trust-region radii: same accept / reject decisions
+        assert relerr(stats[b, :, 0], so[:, 0]) < 1e-6
+    qg, _, taug = gs.solution()
+    qo, _, tauo = oc.solution()
+    assert relerr(qg[0], qo) < 1e-5 and relerr(qg[batch - 1], qo) < 1e-5
