@@ -268,10 +268,15 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     algo_bytes = b_idp_bytes(m.nq, m.nv, T) * B
     achieved = algo_bytes / (stage_ms["id_partials"] * 1e-3) / 1e9
-    traffic = None
+    traffic, fp64 = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(f"id_partials_{args.method}")
+            prof = json.load(f)
+        traffic = prof.get(f"id_partials_{args.method}")
+        flop = prof.get(f"id_partials_{args.method}_fp64_flop")
+        if flop:  # what actually binds this stage: fp64 issue, not HBM
+            fp64 = {"flop_per_launch": flop, "achieved_tflops": flop / (stage_ms["id_partials"] * 1e-3) / 1e12,
+                    "peak_tflops": 148 * 64 * 2 * 1.965e9 / 1e12, "source": "ncu instruction counts, profiles/ncu_traffic.json"}
     except OSError:
         pass
     roofline = {"kernel": "id_partials stage: k_tau_chain<stash> + k_partials_path + k_partials_chain", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -280,7 +285,7 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "note": "arithmetic intensity ~50 fp64 flop/B: this kernel is fp64-issue/latency bound, not HBM "
                         "bound (SURVEY.md §8d); the HBM fraction is reported as BASELINE.json defines it",
-                "stage_ms": stage_ms}
+                "stage_ms": stage_ms, "fp64": fp64}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
