@@ -113,51 +113,37 @@ __device__ __forceinline__ void lu_search(double xc, int c, int lane, double* ub
   ub[c * 32 + lane] = xc;  // U[., c] in the rows chosen before step c (final); unused elsewhere
 }
 
-// Column idx of the concatenation [g[2..W] | x[0..NC-1]] (everything a step updates except the next pivot
-// column g[1], which takes the short path through a shuffle).
-template <int W, int KB, int NC>
-__device__ __forceinline__ double& lu_col(double (&g)[KB], double (&x)[NC], int idx) {
-  return idx < W - 1 ? g[idx + 2] : x[idx - (W - 1 > 0 ? W - 1 : 0)];
-}
-
 template <int KB, int NC, int C0>
 __device__ __forceinline__ void lu_segment(double (&g)[KB], double (&x)[NC], int lane, double* ub, double* pr,
                                            LuState& s) {
   constexpr int W = KB - 1 - C0;  // live columns right of the pivot column at the start of the segment
   constexpr int C1 = C0 + kSeg < KB ? C0 + kSeg : KB;
-  constexpr int NB = (W > 0 ? W - 1 : 0) + NC;  // columns broadcast through shared memory
+  // The pivot row reaches the other rows on two data paths: the trailing columns of G through shuffles
+  // (2 SHFL + 2 MOV per column), the right-hand-side columns through shared memory (lane p stores 16 bytes per
+  // instruction, everybody loads them back as a broadcast).  Measured per pivot step, kb = 25: everything through
+  // shuffles 480 cycles, everything through shared memory 468, this split 440.
+  constexpr int NB = NC;
 #pragma unroll 1
   for (int c = C0; c < C1; ++c) {
     const int p = s.p;
     const double m = s.m;
     double nxt = 0.0;
     if constexpr (W >= 1) nxt = fma(-m, __shfl_sync(kFull, g[1], p), g[1]);
-    // pivot row of the other columns: lane p stores it (16 bytes per instruction), everybody loads it back
-    // as a broadcast.  64-bit shuffles cost 2 SHFL + 2 MOV per column and their dependent-issue stalls
-    // are exposed with one LU warp per scheduler (measured: 480 cycles per step).
     double* b = pr + (c & 1) * ((NB + 1) & ~1);
     if (lane == p) {
 #pragma unroll
-      for (int q = 0; q < NB; q += 2) {
-        const double v0 = lu_col<W>(g, x, q), v1 = q + 1 < NB ? lu_col<W>(g, x, q + 1) : 0.0;
-        *reinterpret_cast<double2*>(b + q) = make_double2(v0, v1);
-      }
+      for (int q = 0; q < NB; q += 2)
+        *reinterpret_cast<double2*>(b + q) = make_double2(x[q], q + 1 < NB ? x[q + 1] : 0.0);
     }
     __syncwarp();
     if (c + 1 < KB) lu_search(nxt, c + 1, lane, ub, s);
-    // update; the g columns move one register to the left on the way (column j of this step is column
-    // j-1 of the next one), which keeps the pivot column in g[0]
-    auto upd = [&](int idx, double pv) {
-      if (idx < W - 1)
-        g[idx + 1] = fma(-m, pv, g[idx + 2]);
-      else
-        x[idx - (W - 1 > 0 ? W - 1 : 0)] = fma(-m, pv, x[idx - (W - 1 > 0 ? W - 1 : 0)]);
-    };
+#pragma unroll
+    for (int j = 2; j <= W; ++j) g[j - 1] = fma(-m, __shfl_sync(kFull, g[j], p), g[j]);
 #pragma unroll
     for (int q = 0; q < NB; q += 2) {
       const double2 v = *reinterpret_cast<const double2*>(b + q);
-      upd(q, v.x);
-      if (q + 1 < NB) upd(q + 1, v.y);
+      x[q] = fma(-m, v.x, x[q]);
+      if (q + 1 < NB) x[q + 1] = fma(-m, v.y, x[q + 1]);
     }
     g[0] = nxt;
   }
