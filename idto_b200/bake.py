@@ -32,7 +32,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_PLANAR, JOINT_QUAT_FLOATING = 0, 1, 2, 3
-GEOM_SPHERE, GEOM_BOX = 0, 1
+GEOM_SPHERE, GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER = 0, 1, 2, 3
+_GEOM_CODE = {"sphere": GEOM_SPHERE, "box": GEOM_BOX, "capsule": GEOM_CAPSULE, "cylinder": GEOM_CYLINDER}
 _JOINT_NQ = {JOINT_REVOLUTE: 1, JOINT_PRISMATIC: 1, JOINT_PLANAR: 3, JOINT_QUAT_FLOATING: 7}
 _JOINT_NV = {JOINT_REVOLUTE: 1, JOINT_PRISMATIC: 1, JOINT_PLANAR: 3, JOINT_QUAT_FLOATING: 6}
 
@@ -312,6 +313,8 @@ class ModelBuilder:
                         shape = ("sphere", [float(child.get("radius")), 0.0, 0.0])
                     elif tag == "box":
                         shape = ("box", list(_vec(child.get("size"))))
+                    elif tag in ("capsule", "cylinder"):  # axis = z of the geometry frame, centred (Drake / URDF)
+                        shape = (tag, [float(child.get("radius")), float(child.get("length")), 0.0])
                     else:
                         shape = (tag, [0.0, 0.0, 0.0])
                     break
@@ -458,10 +461,10 @@ class ModelBuilder:
 
         geoms.sort(key=lambda g: g[0])
         for g in geoms:
-            if g[2] not in ("sphere", "box"):
+            if g[2] not in _GEOM_CODE:
                 raise NotImplementedError(
-                    f"collision shape {g[2]!r} on link {g[6]!r}: only sphere/box have closed-form "
-                    "signed distance here (SURVEY.md §7 'hard parts')")
+                    f"collision shape {g[2]!r} on link {g[6]!r}: only sphere/box/capsule/cylinder have "
+                    "closed-form signed distance here (SURVEY.md §7 'hard parts')")
         # default collision filtering
         def body_parent(bi):
             return bodies[bi]["parent"] if bi >= 0 else None
@@ -485,6 +488,10 @@ class ModelBuilder:
                 ga_groups, gb_groups = link_groups.get(ga[6], set()), link_groups.get(gb[6], set())
                 if any((x, y) in excl for x in ga_groups for y in gb_groups):
                     continue
+                if ga[2] != "sphere" and gb[2] != "sphere":
+                    raise NotImplementedError(
+                        f"collision pair {ga[6]!r} ({ga[2]}) / {gb[6]!r} ({gb[2]}): closed-form signed distance needs "
+                        "a sphere on one side (Drake falls back to FCL for the other pairs)")
                 pairs.append((ia, ib))
 
         quat_starts = [q_start[k] for k, b in enumerate(bodies) if b["jtype"] == JOINT_QUAT_FLOATING]
@@ -500,7 +507,7 @@ class ModelBuilder:
             damping=damping, mass=mass, com=com, inertia=inertia, gravity=self.gravity.copy(),
             actuated=actuated, ngeoms=ng,
             geom_body=np.array([g[1] for g in geoms], np.int32),
-            geom_type=np.array([GEOM_SPHERE if g[2] == "sphere" else GEOM_BOX for g in geoms], np.int32),
+            geom_type=np.array([_GEOM_CODE[g[2]] for g in geoms], np.int32),
             geom_dims=np.array([g[3] for g in geoms], float).reshape(ng, 3),
             X_BG=np.array([g[4].flat() for g in geoms]).reshape(ng, 12),
             npairs=len(pairs),
@@ -551,6 +558,7 @@ def bake_reference_models(reference_root="/root/reference", out_dir=_MODEL_DIR):
     out["acrobot"] = ModelBuilder().add_urdf(os.path.join(mdl, "acrobot", "acrobot.urdf")).finalize()
     out["spinner"] = ModelBuilder().add_urdf(os.path.join(mdl, "spinner_friction.urdf")).finalize()
     out["spinner_sphere"] = ModelBuilder().add_urdf(os.path.join(mdl, "spinner_sphere.urdf")).finalize()
+    out["spinner_capsule"] = ModelBuilder().add_urdf(os.path.join(mdl, "spinner_capsule.urdf")).finalize()
     b = ModelBuilder().add_urdf(os.path.join(mdl, "hopper.urdf"))
     out["hopper_no_ground"] = b.finalize()
     # examples/hopper/hopper.cc:44-50: ground Box(25,25,10) at z=-5 registered on the world body.

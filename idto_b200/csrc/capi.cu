@@ -364,10 +364,13 @@ int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
   }
   const int nb = d->nbodies, ng = d->ngeoms, np = d->npairs;
   for (int i = 0; i < ng; ++i)
-    if (d->geom_type[i] != IDTO_GEOM_SPHERE && d->geom_type[i] != IDTO_GEOM_BOX) return IDTO_ERR_UNSUPPORTED;
+    if (d->geom_type[i] < IDTO_GEOM_SPHERE || d->geom_type[i] > IDTO_GEOM_CYLINDER) {
+      set_last_error("unknown geometry type (sphere, box, capsule, cylinder are supported)");
+      return IDTO_ERR_UNSUPPORTED;
+    }
   for (int i = 0; i < np; ++i)
-    if (d->geom_type[d->pair_geomA[i]] == IDTO_GEOM_BOX && d->geom_type[d->pair_geomB[i]] == IDTO_GEOM_BOX) {
-      set_last_error("box-box contact pairs have no closed-form signed distance here");
+    if (d->geom_type[d->pair_geomA[i]] != IDTO_GEOM_SPHERE && d->geom_type[d->pair_geomB[i]] != IDTO_GEOM_SPHERE) {
+      set_last_error("contact pairs without a sphere on one side have no closed-form signed distance here");
       return IDTO_ERR_UNSUPPORTED;
     }
   auto* m = new idto_model_s();

@@ -148,6 +148,49 @@ __device__ __forceinline__ PointDist point_to_box(V3 size, const M3& R_WG, V3 p_
   const V3 p_WN = mul(R_WG, pn) + p_WG;
   return {dot(grad_W, p_WQ - p_WN), pn, grad_W};
 }
+// Capsule (radius r, length L of the cylindrical part, axis Gz): distance to the segment minus r.
+__device__ __forceinline__ PointDist point_to_capsule(double r, double L, const M3& R_WG, V3 p_WG, V3 p_WQ) {
+  const V3 p = tmul(R_WG, p_WQ - p_WG);
+  const double pz = fmin(fmax(p.z, -0.5 * L), 0.5 * L);
+  const V3 d = {p.x, p.y, p.z - pz};
+  const double dist = sqrt(dot(d, d));
+  const V3 grad_G = dist > 1e-14 ? (1.0 / dist) * d : V3{1, 0, 0};
+  const V3 p_GN = V3{0, 0, pz} + r * grad_G;
+  return {dist - r, p_GN, mul(R_WG, grad_G)};
+}
+// Solid cylinder (radius r, length L, axis Gz): the 2-D box rule on (rho, z) with half sizes (r, L/2).
+__device__ __forceinline__ PointDist point_to_cylinder(double r, double L, const M3& R_WG, V3 p_WG, V3 p_WQ) {
+  const V3 p = tmul(R_WG, p_WQ - p_WG);
+  const double h = 0.5 * L, rho = sqrt(p.x * p.x + p.y * p.y);
+  const double ux = rho > 1e-14 ? p.x / rho : 1.0, uy = rho > 1e-14 ? p.y / rho : 0.0;
+  double ca, cb, ga, gb;
+  if (rho > r || fabs(p.z) > h) {
+    ca = fmin(rho, r), cb = fmin(fmax(p.z, -h), h);
+    const double da = rho - ca, db = p.z - cb, nrm = sqrt(da * da + db * db);
+    ga = da / nrm, gb = db / nrm;
+  } else {
+    const double da = r - rho, db = h - fabs(p.z);
+    if (da <= db) {
+      ca = r, cb = p.z, ga = 1.0, gb = 0.0;
+    } else {
+      const double sg = p.z >= 0 ? 1.0 : -1.0;
+      ca = rho, cb = sg * h, ga = 0.0, gb = sg;
+    }
+  }
+  const V3 p_GN = {ca * ux, ca * uy, cb};
+  const V3 grad_W = mul(R_WG, V3{ga * ux, ga * uy, gb});
+  const V3 p_WN = mul(R_WG, p_GN) + p_WG;
+  return {dot(grad_W, p_WQ - p_WN), p_GN, grad_W};
+}
+// Signed distance from the query point to the shape `type` (dims as in idto_model_desc::geom_dims).
+__device__ __forceinline__ PointDist point_to_shape(int type, V3 dims, const M3& R_WG, V3 p_WG, V3 p_WQ) {
+  switch (type) {
+    case IDTO_GEOM_SPHERE: return point_to_sphere(dims.x, R_WG, p_WG, p_WQ);
+    case IDTO_GEOM_CAPSULE: return point_to_capsule(dims.x, dims.y, R_WG, p_WG, p_WQ);
+    case IDTO_GEOM_CYLINDER: return point_to_cylinder(dims.x, dims.y, R_WG, p_WG, p_WQ);
+    default: return point_to_box(dims, R_WG, p_WG, p_WQ);
+  }
+}
 
 // ------------------------------------------------------------------ shared-memory slabs
 // Position data of one evaluation (SoA, body-minor): written by PositionPhase, read-only afterwards.
@@ -262,14 +305,13 @@ __device__ __forceinline__ void PositionPhase(const SModel& M, const PosSmem& P,
     double distance;
     V3 p_ACa, p_BCb, nhat_BA_W;
     if (M.gtype[gA] == IDTO_GEOM_SPHERE) {
-      const PointDist d = M.gtype[gB] == IDTO_GEOM_SPHERE ? point_to_sphere(dimB.x, R_WGb, p_WGb, p_WGa)
-                                                          : point_to_box(dimB, R_WGb, p_WGb, p_WGa);
+      const PointDist d = point_to_shape(M.gtype[gB], dimB, R_WGb, p_WGb, p_WGa);
       distance = d.distance - dimA.x;
       p_BCb = d.p_GN;
       nhat_BA_W = d.grad_W;
       p_ACa = (-dimA.x) * tmul(R_WGa, d.grad_W);
     } else {
-      const PointDist d = point_to_box(dimA, R_WGa, p_WGa, p_WGb);
+      const PointDist d = point_to_shape(M.gtype[gA], dimA, R_WGa, p_WGa, p_WGb);
       distance = d.distance - dimB.x;
       p_ACa = d.p_GN;
       nhat_BA_W = -d.grad_W;

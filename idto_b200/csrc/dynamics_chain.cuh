@@ -299,14 +299,13 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
         double distance;
         V3 p_ACa, p_BCb, nhat_BA_W;
         if (M.gtype[gA] == IDTO_GEOM_SPHERE) {
-          const PointDist d = M.gtype[gB] == IDTO_GEOM_SPHERE ? point_to_sphere(dimB.x, R_WGb, p_WGb, p_WGa)
-                                                              : point_to_box(dimB, R_WGb, p_WGb, p_WGa);
+          const PointDist d = point_to_shape(M.gtype[gB], dimB, R_WGb, p_WGb, p_WGa);
           distance = d.distance - dimA.x;
           p_BCb = d.p_GN;
           nhat_BA_W = d.grad_W;
           p_ACa = (-dimA.x) * tmul(R_WGa, d.grad_W);
         } else {
-          const PointDist d = point_to_box(dimA, R_WGa, p_WGa, p_WGb);
+          const PointDist d = point_to_shape(M.gtype[gA], dimA, R_WGa, p_WGa, p_WGb);
           distance = d.distance - dimB.x;
           p_ACa = d.p_GN;
           nhat_BA_W = -d.grad_W;

@@ -176,14 +176,13 @@ __device__ __forceinline__ void path_eval(const GModel& M, const SolverConsts& s
         double distance;
         V3 p_ACa, p_BCb, nhat_BA_W;
         if (M.gtype[gA] == IDTO_GEOM_SPHERE) {
-          const PointDist pd = M.gtype[gB] == IDTO_GEOM_SPHERE ? point_to_sphere(dimB.x, R_WGb, p_WGb, p_WGa)
-                                                               : point_to_box(dimB, R_WGb, p_WGb, p_WGa);
+          const PointDist pd = point_to_shape(M.gtype[gB], dimB, R_WGb, p_WGb, p_WGa);
           distance = pd.distance - dimA.x;
           p_BCb = pd.p_GN;
           nhat_BA_W = pd.grad_W;
           p_ACa = (-dimA.x) * tmul(R_WGa, pd.grad_W);
         } else {
-          const PointDist pd = point_to_box(dimA, R_WGa, p_WGa, p_WGb);
+          const PointDist pd = point_to_shape(M.gtype[gA], dimA, R_WGa, p_WGa, p_WGb);
           distance = pd.distance - dimB.x;
           p_ACa = pd.p_GN;
           nhat_BA_W = -pd.grad_W;

@@ -69,6 +69,20 @@ def spinner(T=40, gradients_method=GRAD_FORWARD, max_iterations=200):
     return m, 0.05, prob, params, guess
 
 
+def spinner_capsule(T=40, gradients_method=GRAD_FORWARD, max_iterations=200):
+    """models/spinner_capsule.urdf (finger of spheres against a capsule-shaped spinner) with the spinner example's
+    cost and contact parameters (examples/spinner/spinner.yaml); exercises the sphere-capsule closed form."""
+    m = load_model("spinner_capsule")
+    prob = _make(m, T, 0.05, [0.2, 1.5, 0.0], [0, 0, 0], [0.2, 1.5, 0.0], [0.2, 1.5, 2.0], [1, 1, 1],
+                 [0.1, 0.1, 0.1], [0.1, 0.1, 1e3], [10, 10, 10], [0.1, 0.1, 0.1])
+    params = SolverParameters(max_iterations=max_iterations, scaling=True, equality_constraints=True,
+                              Delta0=1e1, Delta_max=1e5, contact_stiffness=200, dissipation_velocity=0.1,
+                              smoothing_factor=0.01, friction_coefficient=0.5, stiction_velocity=0.05,
+                              gradients_method=gradients_method, verbose=False)
+    guess = [np.array([0.2, 1.5, 0.0]) for _ in range(T + 1)]
+    return m, 0.05, prob, params, guess
+
+
 def hopper(T=50, gradients_method=GRAD_FORWARD, max_iterations=200):
     m = load_model("hopper")
     q0 = [0.61, 0.0, 0.3, -0.5, 0.2]

@@ -239,6 +239,55 @@ inline PointDist point_to_box(V3 size, const M3& R_WG, V3 p_WG, V3 p_WQ) {
   return {dot(grad_W, p_WQ - p_WN), p_GN, grad_W};
 }
 
+// Drake point_distance::DistanceToPoint for a capsule G (radius r, length L of the cylindrical part, axis Gz):
+// distance to the segment [-L/2, L/2] on Gz minus r.  Not used by a BASELINE config; parity unpinned.
+inline PointDist point_to_capsule(double r, double L, const M3& R_WG, V3 p_WG, V3 p_WQ) {
+  const V3 p = tmul(R_WG, p_WQ - p_WG);
+  const double pz = std::min(std::max(p.z, -0.5 * L), 0.5 * L);
+  const V3 d = {p.x, p.y, p.z - pz};
+  const double dist = std::sqrt(dot(d, d));
+  const V3 grad_G = dist > 1e-14 ? (1.0 / dist) * d : V3{1, 0, 0};
+  const V3 p_GN = V3{0, 0, pz} + r * grad_G;
+  return {dist - r, p_GN, R_WG * grad_G};
+}
+
+// Drake point_distance::DistanceToPoint for a solid cylinder G (radius r, length L, axis Gz): the 2-D box
+// rule on (rho, z) with half sizes (r, L/2); inside, the nearer of the side and the caps (side first on ties,
+// like the first-axis rule of the box); on the axis the radial direction is Gx.
+inline PointDist point_to_cylinder(double r, double L, const M3& R_WG, V3 p_WG, V3 p_WQ) {
+  const V3 p = tmul(R_WG, p_WQ - p_WG);
+  const double h = 0.5 * L, rho = std::sqrt(p.x * p.x + p.y * p.y);
+  const double ux = rho > 1e-14 ? p.x / rho : 1.0, uy = rho > 1e-14 ? p.y / rho : 0.0;
+  double ca, cb, ga, gb;
+  if (rho > r || std::fabs(p.z) > h) {
+    ca = std::min(rho, r), cb = std::min(std::max(p.z, -h), h);
+    const double da = rho - ca, db = p.z - cb, nrm = std::sqrt(da * da + db * db);
+    ga = da / nrm, gb = db / nrm;
+  } else {
+    const double da = r - rho, db = h - std::fabs(p.z);
+    if (da <= db) {
+      ca = r, cb = p.z, ga = 1.0, gb = 0.0;
+    } else {
+      const double sg = p.z >= 0 ? 1.0 : -1.0;
+      ca = rho, cb = sg * h, ga = 0.0, gb = sg;
+    }
+  }
+  const V3 p_GN = {ca * ux, ca * uy, cb};
+  const V3 grad_W = R_WG * V3{ga * ux, ga * uy, gb};
+  const V3 p_WN = R_WG * p_GN + p_WG;
+  return {dot(grad_W, p_WQ - p_WN), p_GN, grad_W};
+}
+
+// Signed distance from the query point to the shape `type` (dims as in idto_model_desc::geom_dims).
+inline PointDist point_to_shape(int type, V3 dims, const M3& R_WG, V3 p_WG, V3 p_WQ) {
+  switch (type) {
+    case IDTO_GEOM_SPHERE: return point_to_sphere(dims.x, R_WG, p_WG, p_WQ);
+    case IDTO_GEOM_CAPSULE: return point_to_capsule(dims.x, dims.y, R_WG, p_WG, p_WQ);
+    case IDTO_GEOM_CYLINDER: return point_to_cylinder(dims.x, dims.y, R_WG, p_WG, p_WQ);
+    default: return point_to_box(dims, R_WG, p_WG, p_WQ);
+  }
+}
+
 // ----------------------------------------------------------------------------- inverse dynamics workspace
 struct Kin {
   M3 R_WB[kMaxBodies], R_WF[kMaxBodies];
@@ -334,17 +383,15 @@ static void ContactForces(const Model& M, const ContactParams& cp, Kin* K, int* 
     DistResult pr;
     if (M.gtype[gA] == IDTO_GEOM_SPHERE) {
       // sphere A vs shape B: distance from B to A's centre, minus rA.
-      PointDist d = M.gtype[gB] == IDTO_GEOM_SPHERE
-                        ? point_to_sphere(M.gdims[gB].x, R_WGb, p_WGb, p_WGa)
-                        : point_to_box(M.gdims[gB], R_WGb, p_WGb, p_WGa);
+      PointDist d = point_to_shape(M.gtype[gB], M.gdims[gB], R_WGb, p_WGb, p_WGa);
       const double rA = M.gdims[gA].x;
       pr.distance = d.distance - rA;
       pr.p_BCb = d.p_GN;
       pr.nhat_BA_W = d.grad_W;
       pr.p_ACa = (-rA) * tmul(R_WGa, d.grad_W);
     } else {
-      // shape A (box) vs sphere B: roles swapped, then results swapped back.
-      PointDist d = point_to_box(M.gdims[gA], R_WGa, p_WGa, p_WGb);
+      // shape A (box, capsule, cylinder) vs sphere B: roles swapped, then results swapped back.
+      PointDist d = point_to_shape(M.gtype[gA], M.gdims[gA], R_WGa, p_WGa, p_WGb);
       const double rB = M.gdims[gB].x;
       pr.distance = d.distance - rB;
       pr.p_ACa = d.p_GN;
@@ -1631,6 +1678,18 @@ void oracle_penta_scale(int nb, int k, double* A, double* B, double* C, const do
     std::copy(P.B[i].d.begin(), P.B[i].d.end(), B + size_t(i) * k * k);
     std::copy(P.C[i].d.begin(), P.C[i].d.end(), C + size_t(i) * k * k);
   }
+}
+
+// Test hook: signed distance, nearest surface point (geometry frame) and gradient (world) from the point p_WQ to
+// a shape at pose (R_WG row-major, p_WG).  out = [distance, p_GN(3), grad_W(3)].
+void oracle_point_distance(int type, const double* dims, const double* R_WG, const double* p_WG, const double* p_WQ,
+                           double* out) {
+  M3 R;
+  for (int e = 0; e < 9; ++e) R.m[e] = R_WG[e];
+  const PointDist d = point_to_shape(type, V3{dims[0], dims[1], dims[2]}, R, V3{p_WG[0], p_WG[1], p_WG[2]},
+                                     V3{p_WQ[0], p_WQ[1], p_WQ[2]});
+  out[0] = d.distance, out[1] = d.p_GN.x, out[2] = d.p_GN.y, out[3] = d.p_GN.z;
+  out[4] = d.grad_W.x, out[5] = d.grad_W.y, out[6] = d.grad_W.z;
 }
 
 }  // extern "C"

@@ -58,12 +58,21 @@ def lib():
         L.oracle_penta_solve.argtypes = [ctypes.c_int, ctypes.c_int, _D, _D, _D, _D, ctypes.c_int]
         L.oracle_penta_dense.argtypes = [ctypes.c_int, ctypes.c_int, _D, _D, _D, _D]
         L.oracle_penta_scale.argtypes = [ctypes.c_int, ctypes.c_int, _D, _D, _D, _D]
+        L.oracle_point_distance.argtypes = [ctypes.c_int, _D, _D, _D, _D, _D]
         _LIB = L
     return _LIB
 
 
 def _p(a):
     return a.ctypes.data_as(_D)
+
+
+def point_distance(gtype, dims, R_WG, p_WG, p_WQ):
+    """(distance, p_GN, grad_W) of the restated Drake closed forms (sphere, box, capsule, cylinder)."""
+    a = [np.ascontiguousarray(np.asarray(x, float).reshape(-1)) for x in (dims, R_WG, p_WG, p_WQ)]
+    out = np.zeros(7)
+    lib().oracle_point_distance(int(gtype), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(out))
+    return out[0], out[1:4].copy(), out[4:7].copy()
 
 
 class Oracle:

@@ -1,0 +1,110 @@
+"""Closed-form signed distances (Drake point_distance::DistanceToPoint restated in oracle/idto_oracle.cc and in
+idto_b200/csrc/dynamics.cuh): sphere, box, capsule, cylinder.  No numeric anchor for these exists in the
+reference tree (parity unpinned at the Drake boundary); they are pinned here by brute force — the distance to a
+dense sampling of the surface — and by the properties of a signed distance field (|grad| = 1, the witness point
+lies on the surface along the gradient)."""
+import numpy as np
+import pytest
+
+from idto_b200.bake import GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_SPHERE
+
+
+def _rot(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _surface(gtype, dims, n=120):
+    """Dense sampling of the surface in the geometry frame."""
+    u = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    if gtype == GEOM_SPHERE:
+        th = np.linspace(0, np.pi, n)
+        return np.array([[dims[0] * np.sin(a) * np.cos(b), dims[0] * np.sin(a) * np.sin(b), dims[0] * np.cos(a)]
+                         for a in th for b in u])
+    if gtype == GEOM_BOX:
+        h = np.asarray(dims) / 2
+        g = np.linspace(-1, 1, n // 2)
+        pts = []
+        for ax in range(3):
+            o = [i for i in range(3) if i != ax]
+            for sg in (-1, 1):
+                A, B = np.meshgrid(g * h[o[0]], g * h[o[1]])
+                P = np.zeros((A.size, 3))
+                P[:, ax], P[:, o[0]], P[:, o[1]] = sg * h[ax], A.ravel(), B.ravel()
+                pts.append(P)
+        return np.vstack(pts)
+    r, L = dims[0], dims[1]
+    z = np.linspace(-L / 2, L / 2, n)
+    side = np.array([[r * np.cos(b), r * np.sin(b), zz] for zz in z for b in u])
+    if gtype == GEOM_CYLINDER:
+        rho = np.linspace(0, r, n // 2)
+        caps = np.array([[rr * np.cos(b), rr * np.sin(b), sg * L / 2] for sg in (-1, 1) for rr in rho for b in u])
+        return np.vstack([side, caps])
+    th = np.linspace(0, np.pi / 2, n // 2)
+    caps = np.array([[r * np.cos(a) * np.cos(b), r * np.cos(a) * np.sin(b), sg * (L / 2 + r * np.sin(a))]
+                     for sg in (-1, 1) for a in th for b in u])
+    return np.vstack([side, caps])
+
+
+def _inside(gtype, dims, p):
+    if gtype == GEOM_SPHERE:
+        return np.linalg.norm(p) < dims[0]
+    if gtype == GEOM_BOX:
+        return np.all(np.abs(p) < np.asarray(dims) / 2)
+    r, L = dims[0], dims[1]
+    if gtype == GEOM_CYLINDER:
+        return np.hypot(p[0], p[1]) < r and abs(p[2]) < L / 2
+    return np.linalg.norm(p - [0, 0, np.clip(p[2], -L / 2, L / 2)]) < r
+
+
+@pytest.mark.parametrize("gtype,dims", [(GEOM_SPHERE, [0.3, 0, 0]), (GEOM_BOX, [0.4, 0.6, 0.2]),
+                                        (GEOM_CAPSULE, [0.25, 0.8, 0]), (GEOM_CYLINDER, [0.2, 0.5, 0])])
+def test_point_distance_against_brute_force(oracle_mod, gtype, dims):
+    rng = np.random.default_rng(gtype)
+    S = _surface(gtype, dims)
+    for _ in range(60):
+        R, p_WG = _rot(rng), rng.normal(size=3)
+        p_G = rng.uniform(-0.6, 0.6, 3)
+        p_WQ = R @ p_G + p_WG
+        d, p_GN, grad_W = oracle_mod.point_distance(gtype, dims, R, p_WG, p_WQ)
+        brute = np.min(np.linalg.norm(S - p_G, axis=1)) * (-1 if _inside(gtype, dims, p_G) else 1)
+        assert abs(d - brute) < 2e-2, (p_G, d, brute)          # sampling resolution
+        assert abs(np.linalg.norm(grad_W) - 1) < 1e-12
+        assert np.min(np.linalg.norm(S - p_GN, axis=1)) < 2e-2  # the witness point is on the surface
+        # moving from the witness point along the gradient by the signed distance reaches the query point
+        assert np.allclose(R @ p_GN + p_WG + d * grad_W, p_WQ, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", [0, 1])
+def test_sphere_capsule_contact_matches_oracle(oracle_mod, method):
+    """models/spinner_capsule.urdf: eleven finger spheres against the capsule-shaped spinner, GPU vs oracle."""
+    from idto_b200 import capi, problems
+    m, dt, prob, params, guess = problems.spinner_capsule(gradients_method=method)
+    assert set(m.geom_type.tolist()) == {GEOM_SPHERE, GEOM_CAPSULE} and m.npairs == 11
+    gs = capi.BatchSolver(capi.Model(m), dt, prob, params, 2)
+    oc = oracle_mod.Oracle(m, dt, prob, params)
+    rng = np.random.default_rng(1)
+    q = np.array(guess, float)
+    q[1:] += rng.normal(0, 0.05, q[1:].shape).cumsum(axis=0) * 0.3
+    gs.set_q(q)
+    oc.set_q(q)
+    gs.eval(1)
+    oc.eval(1)
+    v, a = oc.get("v").reshape(-1, m.nv), oc.get("a").reshape(-1, m.nv)
+    active = np.array([oc.inverse_dynamics(q[t + 1], v[t + 1], a[t])[1] for t in range(prob.num_steps)])
+    assert active.any()  # the trajectory does touch the spinner
+    rel = lambda x, y, s=None: np.nanmax(np.abs(x - y)) / (s or max(1.0, np.nanmax(np.abs(y))))
+    assert rel(gs.get("tau")[0], oc.get("tau")) < 1e-11
+    sc = max(1.0, np.nanmax(np.abs(oc.get("dtau_dqp"))))
+    for f in ("dtau_dqm", "dtau_dqt", "dtau_dqp"):
+        assert rel(gs.get(f)[1], oc.get(f), sc) < 2e-6, f
+    gs.set_q(guess)
+    oc.set_q(guess)
+    it, _, stats = gs.solve(15)
+    k, _, so = oc.solve(15)
+    assert np.array_equal(stats[0, :, 1], so[:, 1]) and rel(stats[0, :, 0], so[:, 0]) < 1e-6
