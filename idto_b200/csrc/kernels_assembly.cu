@@ -3,6 +3,8 @@
 // equality-constraint Jacobian bands (cc:1292-1334).  Diagonal cost weights (every reference example;
 // dense weights are rejected at solver creation).  Velocity partials (cc:962-973) are never
 // materialised: dvt_dqt[t] = N+_t/dt and dvt_dqm[t] = -N+_t/dt are applied in place.
+#include <algorithm>
+
 #include "reduce.cuh"
 #include "solver.h"
 
@@ -35,7 +37,7 @@ __device__ __constant__ Prod kProds[8] = {{kN0, kN0, 1}, {kP0, kP0, 1}, {kT0, kT
 // weights 2 dt R / 2 dt Qv / 2 Qf_v are applied to the left operand in registers, in the reference's
 // operation order ((X^T W) Y, cc:1103-1165); the products land in shared memory and are summed in the
 // reference's order.
-__global__ void __launch_bounds__(kAsmThreads) k_assemble(SolverConsts sc, SolverBufs bf, int force) {
+__global__ void __launch_bounds__(kAsmThreads) k_assemble(SolverConsts sc, SolverBufs bf, int force, int alias) {
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) uint64_t bar;
   const int b = blockIdx.x / (sc.T + 1), t = blockIdx.x % (sc.T + 1);
@@ -69,9 +71,12 @@ __global__ void __launch_bounds__(kAsmThreads) k_assemble(SolverConsts sc, Solve
   const int blkp = (blk + 1) & ~1;            // block stride in shared memory (16-byte aligned)
   const int ntl = (nq + kTile - 1) / kTile;   // tiles per side
   const int npad = ntl * kTile;               // padded side of a product
+  // `alias`: every thread has at most one tile, so the products can stay in registers until all reads of the
+  // staged blocks are done and then overwrite them: 27 KB instead of 48 KB per CTA, twice the CTAs per SM
   double* sblk = sm;                          // [kNumBlk][blkp]
-  double* part = sm + kNumBlk * blkp;         // [8][npad * npad] products, column-major
-  double* gpart = part + 8 * npad * npad;     // [6][nq] gradient terms
+  const int nstage = kNumBlk * blkp, nprod = 8 * npad * npad;
+  double* part = alias ? sm : sm + nstage;    // [8][npad * npad] products, column-major
+  double* gpart = sm + (alias ? (nstage > nprod ? nstage : nprod) : nstage + nprod);  // [6][nq] gradient terms
   const double* Np = bf.st.Nplus + size_t(b) * (T + 1) * blk;
   const double* src[kNumBlk];
   src[kP0] = bf.dqp + pb + size_t(t - 1) * blk;
@@ -125,6 +130,15 @@ __global__ void __launch_bounds__(kAsmThreads) k_assemble(SolverConsts sc, Solve
   const int nsym = ntl * (ntl + 1) / 2, nfull = ntl * ntl;
   const int ntask = 5 * nsym + 3 * nfull;
   const bool even = (nv & 1) == 0;
+  double acc[kTile][kTile];
+  int held_k = -1, held_ti = 0, held_tj = 0;
+  auto store_tile = [&](int k, int ti, int tj) {
+    double* out = part + k * npad * npad;
+#pragma unroll
+    for (int u = 0; u < kTile; ++u)
+#pragma unroll
+      for (int v = 0; v < kTile; ++v) out[(tj * kTile + v) * npad + ti * kTile + u] = acc[u][v];
+  };
   for (int task = tid; task < ntask; task += nt) {
     int k, ti, tj;
     if (task < 5 * nsym) {
@@ -139,7 +153,6 @@ __global__ void __launch_bounds__(kAsmThreads) k_assemble(SolverConsts sc, Solve
       const int rem = rem0 - (k - 5) * nfull;
       ti = rem % ntl, tj = rem / ntl;
     }
-    double* out = part + k * npad * npad;
     if (!live(k)) continue;
     const Prod pr = kProds[k];
     const double* A = sblk + pr.left * blkp;
@@ -151,7 +164,10 @@ __global__ void __launch_bounds__(kAsmThreads) k_assemble(SolverConsts sc, Solve
       ia[u] = min(ti * kTile + u, nq - 1) * nv;  // clamped: the padding rows are computed and discarded
       jc[u] = min(tj * kTile + u, nq - 1) * nv;
     }
-    double acc[kTile][kTile] = {};
+#pragma unroll
+    for (int u = 0; u < kTile; ++u)
+#pragma unroll
+      for (int v = 0; v < kTile; ++v) acc[u][v] = 0.0;
     if (even) {
       for (int r = 0; r < nv; r += 2) {
         const double w0 = weight(k, r), w1 = weight(k, r + 1);
@@ -182,10 +198,10 @@ __global__ void __launch_bounds__(kAsmThreads) k_assemble(SolverConsts sc, Solve
         }
       }
     }
-#pragma unroll
-    for (int u = 0; u < kTile; ++u)
-#pragma unroll
-      for (int v = 0; v < kTile; ++v) out[(tj * kTile + v) * npad + ti * kTile + u] = acc[u][v];
+    if (alias)
+      held_k = k, held_ti = ti, held_tj = tj;  // (single trip: ntask <= blockDim)
+    else
+      store_tile(k, ti, tj);
   }
   // ---- gradient terms (cc:1021-1081): six mat-vecs, one (term, column) per thread-task -----------
   const double* q = bf.st.q + (size_t(b) * (T + 1) + t) * nq;
@@ -221,6 +237,10 @@ __global__ void __launch_bounds__(kAsmThreads) k_assemble(SolverConsts sc, Solve
     gpart[term * nq + j] = x;
   }
   __syncthreads();
+  if (alias) {  // all reads of the staged blocks are done: the tiles may overwrite them
+    if (held_k >= 0) store_tile(held_k, held_ti, held_tj);
+    __syncthreads();
+  }
 
   // ---- Hessian bands: sum the products in the reference's order; MakeSymmetric -------------------
   auto P = [&](int k, int i, int j) { return part[k * npad * npad + j * npad + i]; };
@@ -317,14 +337,17 @@ void launch_assemble(const DevModel& dm, const SolverConsts& sc, const SolverBuf
                      cudaStream_t stream) {
   (void)dm;
   const int blkp = (sc.nv * sc.nq + 1) & ~1, npad = (sc.nq + kTile - 1) / kTile * kTile;
-  const int smem = (kNumBlk * blkp + 8 * npad * npad + 6 * sc.nq) * 8;
+  const int ntl = npad / kTile, ntask = 5 * (ntl * (ntl + 1) / 2) + 3 * ntl * ntl;
+  const int alias = ntask <= kAsmThreads ? 1 : 0;
+  const int nstage = kNumBlk * blkp, nprod = 8 * npad * npad;
+  const int smem = ((alias ? std::max(nstage, nprod) : nstage + nprod) + 6 * sc.nq) * 8;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   g_launch_counter += 2;
-  k_assemble<<<sc.B*(sc.T + 1), kAsmThreads, smem, stream>>>(sc, bf, force ? 1 : 0);
+  k_assemble<<<sc.B*(sc.T + 1), kAsmThreads, smem, stream>>>(sc, bf, force ? 1 : 0, alias);
   k_scale<<<sc.B*(sc.T + 1), 128, 0, stream>>>(sc, bf, force ? 1 : 0);
 }
 
