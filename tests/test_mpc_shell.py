@@ -104,3 +104,53 @@ def test_hopper_mpc_resolve_stream_matches_oracle(oracle_mod):
         assert np.max(np.abs(qg[0] - qo2)) < 1e-5 * max(1.0, np.max(np.abs(qo2))), k
         assert np.max(np.abs(qg[1] - qo2)) < 1e-5 * max(1.0, np.max(np.abs(qo2))), k
         assert np.max(np.abs(taug[0] - tauo2)) < 1e-3 * max(1.0, np.max(np.abs(tauo2))), k
+
+
+@pytest.mark.parametrize("N", [2, 3, 4, 7, 40])
+def test_host_spline_of_the_stored_trajectory_matches_scipy(N):
+    from scipy.interpolate import CubicSpline as Ref
+    from idto_b200.mpc import CubicSpline
+    rng = np.random.default_rng(N + 100)
+    h = 0.05
+    y = rng.normal(size=(N + 1, 4)).cumsum(axis=0)
+    mine, ref = CubicSpline(h, y), Ref(np.arange(N + 1) * h, y, bc_type="not-a-knot")
+    for t in np.linspace(0, N * h, 41):
+        assert np.allclose(mine.value(t), ref(t), rtol=1e-10, atol=1e-10)
+    assert np.allclose(mine.value(-1.0), y[0]) and np.allclose(mine.value(N * h + 1.0), y[-1])
+    assert np.allclose(mine.M, mpc_shell.not_a_knot_second_derivatives(y, h), rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_model_predictive_controller_mirror(oracle_mod):
+    """python_examples/mpc_utils.py:87-217 through idto_b200.mpc / idto_b200.pyidto on the hopper: the re-plans
+    of the controller equal the oracle's (restated shell), and the Interpolator samples the stored solution."""
+    from idto_b200 import problems
+    from idto_b200.mpc import Interpolator, ModelPredictiveController
+    from idto_b200.pyidto import BakedPlant, TrajectoryOptimizer
+    from idto_b200.types import GRAD_FORWARD
+    m, dt, prob, params, guess = problems.hopper(T=20, gradients_method=GRAD_FORWARD, max_iterations=2)
+    opt = TrajectoryOptimizer(None, BakedPlant(m, dt), prob, params)
+    mpc = ModelPredictiveController(opt, guess, m.nq, m.nv, mpc_rate=50)
+    oc = oracle_mod.Oracle(m, dt, prob, params)
+    oc.set_q(np.array(guess))
+    oc.solve(2)
+    rng = np.random.default_rng(2)
+    t = 0.0
+    for k in range(4):
+        t += 1.0 / 50
+        qo, vo, _ = oc.solution()
+        el = t - mpc.stored_trajectory.start_time
+        M = mpc_shell.not_a_knot_second_derivatives(qo, dt)
+        q0 = mpc_shell.spline_value(qo, M, dt, el) + rng.normal(0, 1e-3, m.nq)
+        v0 = vo[0] + rng.normal(0, 1e-2, m.nv)
+        oc.reset_initial_conditions(q0, v0)
+        oc.set_q(mpc_shell.shifted_guess(qo, dt, el, q0))
+        oc.solve(2)
+        tr = mpc.UpdateAbstractState(t, np.concatenate((q0, v0)))
+        qo2, vo2, tauo2 = oc.solution()
+        assert tr.start_time == t and np.allclose(tr.q.y, qo2, atol=1e-5 * max(1.0, np.abs(qo2).max())), k
+    B = np.eye(m.nq)[3:]  # the two actuated joints
+    itp = Interpolator(B, B)
+    x = itp.SendState(t + 0.5 * dt, tr)
+    assert x.shape == (4,) and np.allclose(x[:2], B @ tr.q.value(0.5 * dt))
+    assert np.allclose(itp.SendControl(t, tr), B @ tauo2[0], atol=1e-3 * max(1.0, np.abs(tauo2).max()))
