@@ -459,42 +459,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     double* Q = sm;  // n2 x W2 column-major; the sweep buffers are dead
     __syncthreads();
     const int m0 = mid;
-    auto blkY = [&](int i) { return FY + size_t(i) * kk; };
-    auto blkZ = [&](int i) { return FZ + size_t(i) * kk; };
     const bool has_m2 = m0 + 2 <= N, has_mm1 = m0 - 1 >= 0;
+    // stage Y, Z, r of the four rows around the interface (independent, coalesced loads: one L2 round trip; the
+    // element-wise version chased 25 dependent global loads per entry: 22k cycles)
+    double* S = sm + ((n2 * W2 + 1) & ~1);  // [8][kk]: Y, Z of rows m-1, m, m+1, m+2
+    double* Sr = S + 8 * kk;                // [4][kb]
+    {
+      constexpr int NE = (8 * kk + kThreads - 1) / kThreads;  // static trip count: all loads issue before the stores
+      double tmp[NE];
+#pragma unroll
+      for (int k = 0; k < NE; ++k) {
+        const int e = tid + k * kThreads, blk = e / kk, o = e - blk * kk, rowi = m0 - 1 + (blk >> 1);
+        const bool ok = e < 8 * kk && (rowi != m0 - 1 || has_mm1) && (rowi != m0 + 2 || has_m2);
+        tmp[k] = ok ? __ldcg(((blk & 1) ? FZ : FY) + size_t(rowi) * kk + o) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < NE; ++k)
+        if (tid + k * kThreads < 8 * kk) S[tid + k * kThreads] = tmp[k];
+    }
+    for (int e = tid; e < 4 * kb; e += kThreads) {
+      const int rowi = m0 - 1 + e / kb;
+      const bool ok = (rowi != m0 - 1 || has_mm1) && (rowi != m0 + 2 || has_m2);
+      Sr[e] = ok ? Fr[size_t(rowi) * kb + e % kb] : 0.0;
+    }
+    __syncthreads();
+    const double *Ym1 = S, *Zm1 = S + kk, *Ym = S + 2 * kk, *Zm = S + 3 * kk, *Yp1 = S + 4 * kk, *Zp1 = S + 5 * kk,
+                 *Yp2 = S + 6 * kk, *Zp2 = S + 7 * kk;
     for (int e = tid; e < n2 * W2; e += kThreads) {
       const int c = e / n2, rr = e % n2;
-      double val = 0.0;
+      const int br = rr / kb, r1 = rr % kb;
+      // row block 0: x_m row uses Z_m against the bottom chain's row m+2; row block 1: Z'_{m+1} against row m-1
+      const double* Zl = br == 0 ? Zm : Zp1;
+      double val;
       if (c < n2) {
-        const int bc = c / kb, cc = c % kb, br = rr / kb, r1 = rr % kb;
-        if (br == 0 && bc == 0) {          // I - Z_m Z'_{m+2}
-          val = (r1 == cc) ? 1.0 : 0.0;
-          if (has_m2)
-            for (int j = 0; j < kb; ++j) val -= blkZ(m0)[j * kb + r1] * blkZ(m0 + 2)[cc * kb + j];
-        } else if (br == 0 && bc == 1) {   // Y_m - Z_m Y'_{m+2}
-          val = blkY(m0)[cc * kb + r1];
-          if (has_m2)
-            for (int j = 0; j < kb; ++j) val -= blkZ(m0)[j * kb + r1] * blkY(m0 + 2)[cc * kb + j];
-        } else if (br == 1 && bc == 0) {   // Y'_{m+1} - Z'_{m+1} Y_{m-1}
-          val = blkY(m0 + 1)[cc * kb + r1];
-          if (has_mm1)
-            for (int j = 0; j < kb; ++j) val -= blkZ(m0 + 1)[j * kb + r1] * blkY(m0 - 1)[cc * kb + j];
-        } else {                           // I - Z'_{m+1} Z_{m-1}
-          val = (r1 == cc) ? 1.0 : 0.0;
-          if (has_mm1)
-            for (int j = 0; j < kb; ++j) val -= blkZ(m0 + 1)[j * kb + r1] * blkZ(m0 - 1)[cc * kb + j];
+        const int bc = c / kb, cc = c % kb;
+        const double* Rt;  // right factor (column cc) and the leading term
+        if (br == 0 && bc == 0) val = (r1 == cc) ? 1.0 : 0.0, Rt = Zp2;          // I - Z_m Z'_{m+2}
+        else if (br == 0) val = Ym[cc * kb + r1], Rt = Yp2;                      // Y_m - Z_m Y'_{m+2}
+        else if (bc == 0) val = Yp1[cc * kb + r1], Rt = Ym1;                     // Y'_{m+1} - Z'_{m+1} Y_{m-1}
+        else val = (r1 == cc) ? 1.0 : 0.0, Rt = Zm1;                             // I - Z'_{m+1} Z_{m-1}
+        double v2 = 0.0;  // two chains; fully unrolled so that the loads run ahead of the multiply-adds
+#pragma unroll
+        for (int j = 0; j < KB; j += 2) {
+          val -= Zl[j * kb + r1] * Rt[cc * kb + j];
+          if (j + 1 < KB) v2 -= Zl[(j + 1) * kb + r1] * Rt[cc * kb + j + 1];
         }
+        val += v2;
       } else {
-        const int br = rr / kb, r1 = rr % kb;
-        if (br == 0) {
-          val = Fr[size_t(m0) * kb + r1];
-          if (has_m2)
-            for (int j = 0; j < kb; ++j) val -= blkZ(m0)[j * kb + r1] * Fr[size_t(m0 + 2) * kb + j];
-        } else {
-          val = Fr[size_t(m0 + 1) * kb + r1];
-          if (has_mm1)
-            for (int j = 0; j < kb; ++j) val -= blkZ(m0 + 1)[j * kb + r1] * Fr[size_t(m0 - 1) * kb + j];
+        const double* rt = br == 0 ? Sr + 3 * kb : Sr;  // r'_{m+2} or r_{m-1}
+        val = br == 0 ? Sr[kb + r1] : Sr[2 * kb + r1];   // r_m or r'_{m+1}
+        double v2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < KB; j += 2) {
+          val -= Zl[j * kb + r1] * rt[j];
+          if (j + 1 < KB) v2 -= Zl[(j + 1) * kb + r1] * rt[j + 1];
         }
+        val += v2;
       }
       Q[e] = val;
     }
@@ -522,6 +542,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         if (tid == 0) s_ord[p] = c;
         if (rowok && rr != p) {
           const double m = Q[c * n2 + rr] * inv;
+#pragma unroll 4
           for (int j = c + 1 + cg; j < W2; j += NCG) Q[j * n2 + rr] = fma(-m, Q[j * n2 + p], Q[j * n2 + rr]);
         }
         __syncthreads();
@@ -610,7 +631,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 template <int KB>
 static void launch_tw2_kb(const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
   constexpr int LD = (KB + 1) & ~1, kl = KB * LD;
-  const int sweep = 19 * kl + 6 * LD + kLuWarps * KB * 32 + kLuWarps * 2 * (KB + (2 * KB + 1 + kLuWarps - 1) / kLuWarps + 1), tail = std::max(2 * KB * (2 * KB + 1), 3 * (2 * KB * KB + LD) + 2 * LD);
+  const int sweep = 19 * kl + 6 * LD + kLuWarps * KB * 32 + kLuWarps * 2 * (KB + (2 * KB + 1 + kLuWarps - 1) / kLuWarps + 1), tail = std::max(2 * KB * (2 * KB + 1) + 2 + 8 * KB * KB + 4 * KB, 3 * (2 * KB * KB + LD) + 2 * LD);
   const int smem = std::max(sweep, tail) * 8;
   static bool attr_set = false;
   if (!attr_set) {
