@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(128) k_scale(SolverConsts sc, SolverBufs bf, i
   const int T = sc.T, nq = sc.nq, nv = sc.nv, nu = sc.nu, tid = threadIdx.x, nt = blockDim.x;
   const double* D = bf.D + size_t(b) * sc.n;
   const size_t hb = (size_t(b) * (T + 1) + t) * nq * nq;
+#pragma unroll 4
   for (int e = tid; e < nq * nq; e += nt) {
     const int c = e / nq, r = e % nq;
     const double dr = D[t * nq + r];
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(128) k_scale(SolverConsts sc, SolverBufs bf, i
   }
   if (t < T && nu > 0) {
     const size_t pb = (size_t(b) * T + t) * nv * nq, jb = (size_t(b) * T + t) * nu * nq;
+#pragma unroll 2
     for (int e = tid; e < nu * nq; e += nt) {
       const int u = e / nq, c = e % nq, row = sc.unact[u];
       bf.Jp[jb + e] = bf.dqp[pb + size_t(c) * nv + row] * D[(t + 1) * nq + c];

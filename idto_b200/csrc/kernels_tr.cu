@@ -25,7 +25,7 @@ __device__ __forceinline__ void stage_row_blocks(const SolverConsts& sc, const d
 #pragma unroll
   for (int term = 0; term < 5; ++term) {
     const double* p = src[term];
-#pragma unroll 4
+#pragma unroll 8
     for (int e = tid; e < kk; e += nt) hs[term * kk + e] = p ? p[e] : 0.0;
   }
 }
@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
   double* dqs = bf.tmp1 + size_t(b) * n;
   // pU = -(g.g / gHg) g / Delta  (cc:2157)
   double pU2 = 0.0, pH2 = 0.0, a = 0.0, bq = 0.0;
+#pragma unroll 4
   for (int e = tid; e < n; e += nt) {
     const double pu = -(gg / gHg) * gm[e] / Delta, ph = pH[e] / Delta;
     pU2 += pu * pu, pH2 += ph * ph;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
   double dq2 = 0.0, dqH2 = 0.0, gdq = 0.0, q2 = 0.0;
   const double* q = bf.st.q + size_t(b) * n;
   double* qs = bf.sc.q + size_t(b) * n;
+#pragma unroll 4
   for (int e = tid; e < n; e += nt) {
     const double pu = -(gg / gHg) * gm[e] / Delta, ph = pH[e] / Delta;
     double x;
@@ -305,8 +307,11 @@ __global__ void __launch_bounds__(kRowThreads) k_trust_update(SolverConsts sc, S
     // state.AddToQ(dq): the scratch trajectory already holds q+dq and everything derived from it;
     // the reference recomputes the same numbers from scratch (cc:1989-1990 TODO) — we adopt them.
     const int T = sc.T, nq = sc.nq, nv = sc.nv;
+#pragma unroll 4
     for (int e = tid; e < (T + 1) * nq; e += nt) bf.st.q[size_t(b) * (T + 1) * nq + e] = bf.sc.q[size_t(b) * (T + 1) * nq + e];
+#pragma unroll 4
     for (int e = tid; e < (T + 1) * nv; e += nt) bf.st.v[size_t(b) * (T + 1) * nv + e] = bf.sc.v[size_t(b) * (T + 1) * nv + e];
+#pragma unroll 4
     for (int e = tid; e < T * nv; e += nt) {
       bf.st.a[size_t(b) * T * nv + e] = bf.sc.a[size_t(b) * T * nv + e];
       bf.st.tau[size_t(b) * T * nv + e] = bf.sc.tau[size_t(b) * T * nv + e];
