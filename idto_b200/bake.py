@@ -354,6 +354,108 @@ class ModelBuilder:
                     self.filter_excludes.append((gname, ig))
         return self
 
+    def add_sdf(self, path):
+        """`Parser(plant).AddModels(sdf)` analogue for single-model SDF 1.7 files (models/allegro_hand.sdf).
+
+        SDF semantics restated: a link `<pose>` is expressed in the model frame; a joint frame coincides with
+        its child link frame (no joint `<pose>` in this file); `<axis><xyz expressed_in="__model__">` is given
+        in the model frame; `<inertial><pose>` places the centre of mass and the inertia axes in the link
+        frame; joints with a non-zero effort limit get an actuator (Drake's SDF parser).  When a collision
+        `<geometry>` lists several shapes (palm: `<sphere>` and `<box>`, allegro_hand.sdf:47-56) sdformat's
+        Geometry::Load keeps the first match of its fixed order box, capsule, cylinder, ellipsoid, plane,
+        sphere — the box."""
+        with open(path) as f:
+            text = f.read()
+        if "drake:" in text and "xmlns:drake" not in text:
+            text = text.replace("<sdf ", '<sdf xmlns:drake="http://drake.mit.edu" ', 1)
+        model = ET.fromstring(text).find("model")
+        self.name = model.get("name", self.name)
+
+        def pose(node):
+            pn = node.find("pose") if node is not None else None
+            if pn is None or not (pn.text or "").strip():
+                return X()
+            v = [float(t) for t in pn.text.split()]
+            return X(rpy_to_R(*v[3:6]), v[:3])
+
+        X_ML = {}
+        for ln in model.findall("link"):
+            link = _Link(ln.get("name"))
+            X_ML[link.name] = pose(ln)
+            inr = ln.find("inertial")
+            if inr is not None:
+                Xi = pose(inr)
+                link.mass = float(inr.findtext("mass", "0"))
+                link.com = Xi.p.copy()
+                it = inr.find("inertia")
+                if it is not None:
+                    g = lambda k: float(it.findtext(k, "0"))
+                    I = np.array([[g("ixx"), g("ixy"), g("ixz")], [g("ixy"), g("iyy"), g("iyz")],
+                                  [g("ixz"), g("iyz"), g("izz")]])
+                    link.I_cm = Xi.R @ I @ Xi.R.T
+            for col in ln.findall("collision"):
+                geo = col.find("geometry")
+                shape = None
+                for tag in ("box", "capsule", "cylinder", "ellipsoid", "plane", "sphere"):
+                    ch = geo.find(tag)
+                    if ch is None:
+                        continue
+                    if tag == "box":
+                        shape = ("box", [float(t) for t in ch.findtext("size").split()])
+                    elif tag == "sphere":
+                        shape = ("sphere", [float(ch.findtext("radius")), 0.0, 0.0])
+                    elif tag in ("capsule", "cylinder"):
+                        shape = (tag, [float(ch.findtext("radius")), float(ch.findtext("length")), 0.0])
+                    else:
+                        shape = (tag, [0.0, 0.0, 0.0])
+                    break
+                link.collisions.append((self._next_geom, shape[0], shape[1], pose(col),
+                                        col.get("name", f"{link.name}_collision{len(link.collisions)}")))
+                self._next_geom += 1
+            self.links[link.name] = link
+            self.link_order.append(link.name)
+        for jn in model.findall("joint"):
+            parent, child = jn.findtext("parent"), jn.findtext("child")
+            ax = jn.find("axis")
+            axis_in, frame = np.array([0.0, 0.0, 1.0]), ""
+            damping, effort = np.zeros(1), None
+            if ax is not None:
+                xyz = ax.find("xyz")
+                axis_in = np.array([float(t) for t in xyz.text.split()])
+                frame = xyz.get("expressed_in", "")
+                dyn = ax.find("dynamics")
+                if dyn is not None and dyn.findtext("damping"):
+                    damping = np.array([float(dyn.findtext("damping"))])
+                lim = ax.find("limit")
+                if lim is not None and lim.findtext("effort"):
+                    effort = float(lim.findtext("effort"))
+            X_MC, X_MP = X_ML[child], X_ML.get(parent, X())
+            axis = X_MC.R.T @ axis_in if frame == "__model__" else axis_in  # joint frame == child link frame
+            axis = axis / np.linalg.norm(axis)
+            jtype = {"revolute": "revolute", "prismatic": "prismatic", "fixed": "fixed"}[jn.get("type")]
+            self.joints.append(_Joint(jn.get("name"), jtype, parent, child, X_MP.inv() @ X_MC, axis, damping, effort,
+                                      len(self.joints)))
+            if jtype != "fixed" and not (effort is not None and effort == 0.0):
+                self.actuated_joints.add(jn.get("name"))
+        self._sdf_root_links = [n for n in X_ML if n not in {j.child for j in self.joints}]
+        self._sdf_X_ML = X_ML
+        return self
+
+    def weld_frames(self, parent_link, child_link, X_PC):
+        """plant.WeldFrames(parent_frame, child_frame, X_PC) analogue (a fixed joint)."""
+        self.joints.append(_Joint(f"weld_{child_link}", "fixed", parent_link, child_link, X_PC, np.array([0.0, 0.0, 1.0]),
+                                  np.zeros(1), None, len(self.joints)))
+        return self
+
+    def add_rigid_body(self, name, mass, com, I_cm):
+        """plant.AddRigidBody(name, SpatialInertia) analogue: a free body gets a quaternion floating joint at
+        Finalize (after every declared joint)."""
+        link = _Link(name)
+        link.mass, link.com, link.I_cm = float(mass), np.asarray(com, float), np.asarray(I_cm, float)
+        self.links[name] = link
+        self.link_order.append(name)
+        return self
+
     def register_collision_geometry(self, link, X_LG, shape, dims, name="geom"):
         """plant.RegisterCollisionGeometry(body, X_BG, shape, name, ...) analogue."""
         d = list(dims) + [0.0] * (3 - len(dims))
@@ -476,15 +578,19 @@ class ModelBuilder:
         for a, b in self.filter_excludes:
             excl.add((a, b))
             excl.add((b, a))
+        adjacent = {(j.parent, j.child) for j in self.joints if j.type != "fixed" and j.parent != "world"}
         pairs = []
         for ia in range(len(geoms)):
             for ib in range(ia + 1, len(geoms)):
                 ga, gb = geoms[ia], geoms[ib]
                 ba, bb = ga[1], gb[1]
                 if ba == bb:
-                    continue  # same (merged) body, or both anchored to the world
-                if (ba >= 0 and bodies[ba]["parent"] == bb) or (bb >= 0 and bodies[bb]["parent"] == ba):
-                    continue  # adjacent bodies (connected by a joint)
+                    continue  # same welded subgraph (merged body), or both anchored to the world
+                # MultibodyPlant::ApplyDefaultCollisionFilters: the two bodies of a joint do not collide, except
+                # when the joint's parent is the world itself or the joint is a free body's floating joint (a
+                # ball may touch a palm that is welded to the world; a link may not touch the link it hinges on)
+                if (ga[6], gb[6]) in adjacent or (gb[6], ga[6]) in adjacent:
+                    continue
                 ga_groups, gb_groups = link_groups.get(ga[6], set()), link_groups.get(gb[6], set())
                 if any((x, y) in excl for x in ga_groups for y in gb_groups):
                     continue
@@ -566,6 +672,13 @@ def bake_reference_models(reference_root="/root/reference", out_dir=_MODEL_DIR):
     b.register_collision_geometry("world", X(p=[0.0, 0.0, -5.0]), "box", [25.0, 25.0, 10.0], "ground")
     out["hopper"] = b.finalize()
     out["mini_cheetah"] = ModelBuilder().add_urdf(os.path.join(mdl, "mini_cheetah_with_ground.urdf")).finalize()
+    # examples/allegro_hand/allegro_hand.cc:83-113: hand welded to the world with RPY(0, -pi/2, 0), free ball
+    # (m = 0.05 kg, r = 0.06 m, solid sphere) with one collision sphere, registered after the hand's geometries
+    b = ModelBuilder().add_sdf(os.path.join(mdl, "allegro_hand.sdf"))
+    b.weld_frames("world", "hand_root", X(rpy_to_R(0.0, -math.pi / 2, 0.0), [0.0, 0.0, 0.0]))
+    b.add_rigid_body("ball", 0.05, [0.0, 0.0, 0.0], 0.4 * 0.05 * 0.06 ** 2 * np.eye(3))
+    b.register_collision_geometry("ball", X(), "sphere", [0.06], "ball_collision")
+    out["allegro_hand"] = b.finalize()
     for k, m in out.items():
         m.name = k
         m.save(os.path.join(out_dir, k + ".json"))

@@ -597,6 +597,12 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
     set_last_error("gradients_method must be forward, central or central4 (autodiff needs Drake scalars)");
     return IDTO_ERR_UNSUPPORTED;
   }
+  if (use_chain_kernels(m->dm) && chain_min_smem_bytes(m->dm, nv, p->gradients_method) > 226 * 1024) {
+    set_last_error("model needs " + std::to_string(chain_min_smem_bytes(m->dm, nv, p->gradients_method) / 1024) +
+                   " KB of shared memory per inverse-dynamics CTA (" + std::to_string(m->dm.np) +
+                   " candidate contact pairs): more than an SM has; the per-evaluation pair list is not pruned yet");
+    return IDTO_ERR_UNSUPPORTED;
+  }
   auto* s = new idto_solver_s();
   s->model = m, s->params = *p;
   cudaGetDevice(&s->device);

@@ -303,6 +303,17 @@ static int chain_key(const DevModel& dm) {
     default: break;                               \
   }
 
+// Shared memory one CTA of the ID kernels needs for this model (a single slot is the minimum): the contact-pair
+// scratch is sized by the number of CANDIDATE pairs, so models with hundreds of pairs (allegro hand: 187) do
+// not fit until the pair list is pruned per evaluation.
+int chain_min_smem_bytes(const DevModel& dm, int nv, int method) {
+  const int ntau = method == IDTO_GRAD_CENTRAL4 ? 3 : 2;
+  const int ncol = dm.nfull > 0 ? dm.nfull : 1;
+  const int partials = model_smem_bytes(dm) + 8 * nv + 8 * (2 * 2 * cpose_doubles(dm) + (ncol + 1) * cgroup_doubles(dm, nv, ntau));
+  const int tau = model_smem_bytes(dm) + (64 / dm.cgroup) * cgroup_doubles(dm, nv, 1) * 8;
+  return partials > tau ? partials : tau;
+}
+
 bool chain_supported(const DevModel& dm) {
   if (!dm.chain_ok) return false;
   switch (chain_key(dm)) {

@@ -126,6 +126,7 @@ int launch_mpc_advance(const SolverConsts& sc, const SolverBufs& b, const double
                        cudaStream_t stream);
 int partials_smem_bytes(const DevModel& dm, int nq);
 bool chain_supported(const DevModel& dm);
+int chain_min_smem_bytes(const DevModel& dm, int nv, int method);  // one-slot CTA of the chain-lane ID kernels
 void launch_partials_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
                            cudaStream_t stream);
 // single-lane subtree evaluations for the path columns (after launch_stash_chain filled bf.stash)

@@ -116,6 +116,27 @@ def mini_cheetah(T=40, gradients_method=GRAD_CENTRAL, max_iterations=1):
     return m, 0.05, prob, params, guess
 
 
+_ALLEGRO_Q0 = [-0.1, 1.0, 1.0, 1.0, 0.6, 1.9, 1.0, 1.0, 0.0, 0.7, 1.0, 1.0, 0.1, 1.0, 1.0, 1.0,
+               1.0, 0.0, 0.0, 0.0, -0.06, 0.0, 0.07]
+
+
+def allegro_hand(T=60, gradients_method=GRAD_FORWARD, max_iterations=1):
+    """examples/allegro_hand/allegro_hand.yaml:8-125 (in-hand rotation of a free ball: 16 finger joints + the
+    ball's quaternion and position; 188 candidate contact pairs), num_steps overridden to the BASELINE horizon."""
+    m = load_model("allegro_hand")
+    qn = list(_ALLEGRO_Q0)
+    qn[16:20] = [0.7, 0.0, 0.0, -0.7]
+    prob = _make(m, T, 0.05, _ALLEGRO_Q0, [0.0] * 22, qn, qn,
+                 [1e-2] * 16 + [1e1] * 7, [1e-3] * 16 + [1e0] * 6, [1e-1] * 16 + [1e3] * 6,
+                 [1e0] * 16 + [1e2] * 7, [1e1] * 22)
+    params = SolverParameters(max_iterations=max_iterations, scaling=True, equality_constraints=True,
+                              contact_stiffness=100, dissipation_velocity=0.1, smoothing_factor=0.001,
+                              friction_coefficient=1.0, stiction_velocity=0.1,
+                              gradients_method=gradients_method, verbose=False)
+    guess = [np.array(_ALLEGRO_Q0) for _ in range(T + 1)]
+    return m, 0.05, prob, params, guess
+
+
 def pendulum(T=20, dt=0.05, gradients_method=GRAD_FORWARD):
     """optimizer/test/trajectory_optimizer_test.cc:434-490 (PendulumSwingup)."""
     m = load_model("pendulum")
