@@ -22,7 +22,7 @@ _I = ctypes.POINTER(ctypes.c_int)
 _LIB = None
 
 ERRORS = {-1: "invalid argument", -2: "unsupported", -3: "CUDA error", -4: "factorisation failed",
-          -5: "no CUDA device (no CPU fallback)"}
+          -5: "no CUDA device (no CPU fallback)", -6: "too many simultaneous contacts"}
 
 
 class IdtoError(RuntimeError):

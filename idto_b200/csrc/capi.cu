@@ -320,7 +320,11 @@ int check_status(idto_solver_s* s) {
   IDTO_CUDA_CHECK(cudaStreamSynchronize(s->stream));
   const int st = *s->status_host;
   if (st != 0) {
-    set_last_error("penta-diagonal factorisation failed (singular diagonal block)");
+    if (st == IDTO_ERR_CONTACT_OVERFLOW)
+      set_last_error("more than " + std::to_string(kMaxActivePairs) +
+                     " contact pairs within the activation distance in one inverse-dynamics evaluation");
+    else
+      set_last_error("penta-diagonal factorisation failed (singular diagonal block)");
     int zero = 0;
     cudaMemcpyAsync(s->bf.status, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream);
     return st;
@@ -409,6 +413,8 @@ int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
   };
   DevModel& dm = m->dm;
   dm.nb = nb, dm.nbp = nbp, dm.nq = d->nq, dm.nv = d->nv, dm.ng = ngp, dm.np = np, dm.npp = npp;
+  dm.prune = np > kMaxActivePairs ? 1 : 0;
+  dm.nact = dm.prune ? kMaxActivePairs : npp;
   dm.nlevels = nlevels, dm.group = G;
   dm.gx = d->gravity[0], dm.gy = d->gravity[1], dm.gz = d->gravity[2];
   std::vector<int> parent_p(nbp, -1);
@@ -597,11 +603,20 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
     set_last_error("gradients_method must be forward, central or central4 (autodiff needs Drake scalars)");
     return IDTO_ERR_UNSUPPORTED;
   }
-  if (use_chain_kernels(m->dm) && chain_min_smem_bytes(m->dm, nv, p->gradients_method) > 226 * 1024) {
-    set_last_error("model needs " + std::to_string(chain_min_smem_bytes(m->dm, nv, p->gradients_method) / 1024) +
-                   " KB of shared memory per inverse-dynamics CTA (" + std::to_string(m->dm.np) +
-                   " candidate contact pairs): more than an SM has; the per-evaluation pair list is not pruned yet");
-    return IDTO_ERR_UNSUPPORTED;
+  {
+    const bool chain = use_chain_kernels(m->dm);
+    if (m->dm.prune && !chain) {
+      set_last_error("models with more than " + std::to_string(kMaxActivePairs) +
+                     " candidate contact pairs need the chain-lane inverse-dynamics kernels");
+      return IDTO_ERR_UNSUPPORTED;
+    }
+    const int need = chain ? chain_min_smem_bytes(m->dm, nv, p->gradients_method) : partials_smem_bytes(m->dm, nq);
+    if (need > 226 * 1024) {
+      set_last_error("model needs " + std::to_string(need / 1024) + " KB of shared memory per inverse-dynamics CTA (" +
+                     std::to_string(m->dm.np) + " candidate contact pairs, " + std::to_string(m->dm.nact) +
+                     " pair slots per evaluation): more than an SM has");
+      return IDTO_ERR_UNSUPPORTED;
+    }
   }
   auto* s = new idto_solver_s();
   s->model = m, s->params = *p;
@@ -667,6 +682,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   bf.q_init = s->q_init, bf.v_init = s->v_init, bf.q_nom = s->q_nom, bf.v_nom = s->v_nom;
   bf.stats = nullptr, bf.stats_cap = 0;
   sc.Qq = dQq, sc.Qv = dQv, sc.Qfq = dQfq, sc.Qfv = dQfv, sc.R = dR, sc.unact = dun, sc.quat_starts = dqs;
+  sc.status = bf.status;
   auto up_diag = [&](double* dst, const double* Mx, int n) {
     std::vector<double> dg(n);
     for (int i = 0; i < n; ++i) dg[i] = Mx[size_t(i) * n + i];

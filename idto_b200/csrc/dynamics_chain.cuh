@@ -20,6 +20,7 @@ struct CModel {  // baked tables in shared memory (superset of SModel)
   const int *levbody, *levcross, *plane, *gslot, *gdyn, *bchain;
   const double* XWGs;
   int ngb, ngd, nlev;
+  int nact, prune;  // pair slots per evaluation; prune: slots hold the compacted ACTIVE pairs, not every candidate
 };
 __device__ __forceinline__ CModel make_cmodel(const DevModel& dm, const int* si, const double* sd) {
   CModel C;
@@ -28,6 +29,7 @@ __device__ __forceinline__ CModel make_cmodel(const DevModel& dm, const int* si,
   C.gslot = si + dm.o_gslot, C.gdyn = si + dm.o_gdyn, C.bchain = si + dm.o_bchain;
   C.XWGs = sd + dm.o_XWGs;
   C.ngb = dm.ngb, C.ngd = dm.ngd, C.nlev = dm.nlevels;
+  C.nact = dm.nact, C.prune = dm.prune;
   return C;
 }
 
@@ -38,7 +40,7 @@ struct PoseSmem {
   double* PWB;  // [3][nb]
   double* RWF;  // [9][nb]
   double* GP;   // [12][ngd] world pose of geometries on moving bodies
-  double* PG;   // [7][npp]  nhat(3) p_WC(3) fn_c(1)
+  double* PG;   // [7][nact]  nhat(3) p_WC(3) fn_c(1); pruned models: + [nact] candidate index of each slot, [1] count
 };
 // Per-evaluation scratch.
 struct EvalSmem {
@@ -46,16 +48,17 @@ struct EvalSmem {
   double* P;    // [3][nb] p_WB  (copy; the pose may be shared)
   double* AX;   // [3][nb] joint axis in W (1-dof joints)
   double* BV;   // [6][ngb] w, v of geometry-carrying bodies
-  double* PF;   // [3][npp] contact force of each pair
+  double* PF;   // [3][nact] contact force of each pair slot
 };
-__host__ __device__ inline int cpose_doubles(const DevModel& dm) { return 21 * dm.nb + 12 * (dm.ngd > 0 ? dm.ngd : 1) + 7 * dm.npp; }
+__host__ __device__ inline int cpair_doubles(const DevModel& dm) { return 7 * dm.nact + (dm.prune ? dm.nact + 2 : 0); }
+__host__ __device__ inline int cpose_doubles(const DevModel& dm) { return 21 * dm.nb + 12 * (dm.ngd > 0 ? dm.ngd : 1) + cpair_doubles(dm); }
 // private pose part of a full evaluation: geometry poses + pair geometry only
-__host__ __device__ inline int cpose_private_doubles(const DevModel& dm) { return 12 * (dm.ngd > 0 ? dm.ngd : 1) + 7 * dm.npp; }
+__host__ __device__ inline int cpose_private_doubles(const DevModel& dm) { return 12 * (dm.ngd > 0 ? dm.ngd : 1) + cpair_doubles(dm); }
 __device__ __forceinline__ PoseSmem make_cpose_private(const DevModel& dm, double* b) {
   const int ngd = dm.ngd > 0 ? dm.ngd : 1;
   return {nullptr, nullptr, nullptr, b, b + 12 * ngd};
 }
-__host__ __device__ inline int ceval_doubles(const DevModel& dm) { return 12 * dm.nb + 6 * (dm.ngb > 0 ? dm.ngb : 1) + 3 * dm.npp; }
+__host__ __device__ inline int ceval_doubles(const DevModel& dm) { return 12 * dm.nb + 6 * (dm.ngb > 0 ? dm.ngb : 1) + 3 * dm.nact; }
 __device__ __forceinline__ PoseSmem make_cpose(const DevModel& dm, double* b) {
   const int ngd = dm.ngd > 0 ? dm.ngd : 1;
   return {b, b + 9 * dm.nb, b + 12 * dm.nb, b + 21 * dm.nb, b + 21 * dm.nb + 12 * ngd};
@@ -71,6 +74,60 @@ struct BodyState {
 };
 __device__ __forceinline__ double shfl_d(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 __device__ __forceinline__ V3 shfl_v(V3 a, int src) { return {shfl_d(a.x, src), shfl_d(a.y, src), shfl_d(a.z, src)}; }
+
+// Geometry of candidate pair ip at the pose in `Po` (cc:272-320): signed distance, contact normal (from A into B,
+// negated: the direction of the force on B), contact point (midpoint of the witness points).
+struct PairGeom {
+  double distance;
+  V3 nhat, p_WC;
+};
+__device__ __forceinline__ PairGeom pair_geometry(const CModel& C, const PoseSmem& Po, int ip) {
+  const SModel& M = C.M;
+  const int gA = M.pA[ip], gB = M.pB[ip];
+  M3 R_WGa, R_WGb;
+  V3 p_WGa, p_WGb;
+  if (M.gbody[gA] >= 0) {
+    R_WGa = load_R(Po.GP, C.ngd, C.gdyn[gA]), p_WGa = load_V(Po.GP + 9 * C.ngd, C.ngd, C.gdyn[gA]);
+  } else {
+    R_WGa = load_R(C.XWGs, M.ng, gA), p_WGa = load_V(C.XWGs + 9 * M.ng, M.ng, gA);
+  }
+  if (M.gbody[gB] >= 0) {
+    R_WGb = load_R(Po.GP, C.ngd, C.gdyn[gB]), p_WGb = load_V(Po.GP + 9 * C.ngd, C.ngd, C.gdyn[gB]);
+  } else {
+    R_WGb = load_R(C.XWGs, M.ng, gB), p_WGb = load_V(C.XWGs + 9 * M.ng, M.ng, gB);
+  }
+  const V3 dimA = load_V(M.gdims, M.ng, gA), dimB = load_V(M.gdims, M.ng, gB);
+  PairGeom r;
+  V3 p_ACa, p_BCb, nhat_BA_W;
+  if (M.gtype[gA] == IDTO_GEOM_SPHERE) {
+    const PointDist d = point_to_shape(M.gtype[gB], dimB, R_WGb, p_WGb, p_WGa);
+    r.distance = d.distance - dimA.x;
+    p_BCb = d.p_GN;
+    nhat_BA_W = d.grad_W;
+    p_ACa = (-dimA.x) * tmul(R_WGa, d.grad_W);
+  } else {
+    const PointDist d = point_to_shape(M.gtype[gA], dimA, R_WGa, p_WGa, p_WGb);
+    r.distance = d.distance - dimB.x;
+    p_ACa = d.p_GN;
+    nhat_BA_W = -d.grad_W;
+    p_BCb = (-dimB.x) * tmul(R_WGb, d.grad_W);
+  }
+  r.nhat = -nhat_BA_W;
+  r.p_WC = 0.5 * ((mul(R_WGa, p_ACa) + p_WGa) + (mul(R_WGb, p_BCb) + p_WGb));
+  return r;
+}
+// candidate index held by slot `is` of a pruned pair list (clamped: the padding groups of a CTA share one
+// scratch area, so what they read back may be another group's list)
+__device__ __forceinline__ int slot_pair(const double* ids, int is, int np) {
+  const int ip = int(ids[is]);
+  return ip < 0 ? 0 : (ip < np ? ip : np - 1);
+}
+// compliant normal force at signed distance d (cc:349-359); 0 outside the activation distance (cc:268-275)
+__device__ __forceinline__ double contact_fn_c(const SolverConsts& sc, double distance) {
+  if (!(distance <= sc.threshold)) return 0.0;
+  const double exponent = -distance / sc.sigma;
+  return exponent >= 37 ? -sc.k * distance : sc.sigma * sc.k * log(1 + exp(exponent));
+}
 
 // Perturbation of the inputs of one evaluation (finite differencing of column i): applied to the owner
 // body's joint only.  q[local] += dq; v += cv * Ncol_v; a += ca * Ncol_a, where a column of N+ is either
@@ -278,55 +335,56 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
   __syncwarp();
 
   // ---- contact pairs: geometry (cc:272-320, 349-359) and forces (cc:322-373), one pair per lane ---------
+  // Pair slots: slot == candidate index when every candidate has one (C.prune == 0); otherwise the active pairs
+  // (distance <= threshold, exactly the pairs the reference visits, cc:272-275) compacted in candidate order,
+  // which keeps the order the forces are summed in (cc:376-384).
+  const int pst = C.nact;
+  double* const ids = Po.PG + 7 * pst;  // pruned: candidate index of each slot, then the slot count
   if ((kPose || kBias) && M.np > 0) {
-    for (int ip = c; ip < M.np; ip += CG) {
-      const int gA = M.pA[ip], gB = M.pB[ip];
-      const int bA = M.gbody[gA], bB = M.gbody[gB];
-      if (kPose) {
-        M3 R_WGa, R_WGb;
-        V3 p_WGa, p_WGb;
-        if (bA >= 0) {
-          R_WGa = load_R(Po.GP, C.ngd, C.gdyn[gA]), p_WGa = load_V(Po.GP + 9 * C.ngd, C.ngd, C.gdyn[gA]);
-        } else {
-          R_WGa = load_R(C.XWGs, M.ng, gA), p_WGa = load_V(C.XWGs + 9 * M.ng, M.ng, gA);
+    if (kPose) {
+      if (C.prune) {
+        int count = 0;
+        for (int ip0 = 0; ip0 < M.np; ip0 += CG) {
+          const int ip = ip0 + c;
+          PairGeom pg;
+          bool act = false;
+          if (ip < M.np) {
+            pg = pair_geometry(C, Po, ip);
+            act = pg.distance <= sc.threshold;
+          }
+          const unsigned grp = (__ballot_sync(0xffffffffu, act) >> gbase) & (CG == 32 ? 0xffffffffu : ((1u << (CG & 31)) - 1u));
+          const int pos = count + __popc(grp & ((1u << c) - 1u));
+          if (act && pos < pst) {
+            store_V(Po.PG, pst, pos, pg.nhat);
+            store_V(Po.PG + 3 * pst, pst, pos, pg.p_WC);
+            Po.PG[6 * pst + pos] = contact_fn_c(sc, pg.distance);
+            ids[pos] = double(ip);
+          }
+          count += __popc(grp);
         }
-        if (bB >= 0) {
-          R_WGb = load_R(Po.GP, C.ngd, C.gdyn[gB]), p_WGb = load_V(Po.GP + 9 * C.ngd, C.ngd, C.gdyn[gB]);
-        } else {
-          R_WGb = load_R(C.XWGs, M.ng, gB), p_WGb = load_V(C.XWGs + 9 * M.ng, M.ng, gB);
+        if (c == 0) {
+          ids[pst] = double(count < pst ? count : pst);
+          if (count > pst) atomicExch(sc.status, IDTO_ERR_CONTACT_OVERFLOW);
         }
-        const V3 dimA = load_V(M.gdims, M.ng, gA), dimB = load_V(M.gdims, M.ng, gB);
-        double distance;
-        V3 p_ACa, p_BCb, nhat_BA_W;
-        if (M.gtype[gA] == IDTO_GEOM_SPHERE) {
-          const PointDist d = point_to_shape(M.gtype[gB], dimB, R_WGb, p_WGb, p_WGa);
-          distance = d.distance - dimA.x;
-          p_BCb = d.p_GN;
-          nhat_BA_W = d.grad_W;
-          p_ACa = (-dimA.x) * tmul(R_WGa, d.grad_W);
-        } else {
-          const PointDist d = point_to_shape(M.gtype[gA], dimA, R_WGa, p_WGa, p_WGb);
-          distance = d.distance - dimB.x;
-          p_ACa = d.p_GN;
-          nhat_BA_W = -d.grad_W;
-          p_BCb = (-dimB.x) * tmul(R_WGb, d.grad_W);
+        __syncwarp();
+      } else {
+        for (int ip = c; ip < M.np; ip += CG) {
+          const PairGeom pg = pair_geometry(C, Po, ip);
+          store_V(Po.PG, pst, ip, pg.nhat);
+          store_V(Po.PG + 3 * pst, pst, ip, pg.p_WC);
+          Po.PG[6 * pst + ip] = contact_fn_c(sc, pg.distance);
         }
-        double fn_c = 0.0;
-        if (distance <= sc.threshold) {
-          const double exponent = -distance / sc.sigma;
-          fn_c = exponent >= 37 ? -sc.k * distance : sc.sigma * sc.k * log(1 + exp(exponent));
-        }
-        const V3 nhat = -nhat_BA_W;
-        const V3 p_WC = 0.5 * ((mul(R_WGa, p_ACa) + p_WGa) + (mul(R_WGb, p_BCb) + p_WGb));
-        store_V(Po.PG, M.npp, ip, nhat);
-        store_V(Po.PG + 3 * M.npp, M.npp, ip, p_WC);
-        Po.PG[6 * M.npp + ip] = fn_c;
       }
-      if (kBias) {
-        const double fn_c = Po.PG[6 * M.npp + ip];
+    }
+    if (kBias) {
+      const int nslot = C.prune ? min(int(ids[pst]), pst) : M.np;
+      for (int is = c; is < nslot; is += CG) {
+        const int ip = C.prune ? slot_pair(ids, is, M.np) : is;
+        const int bA = M.gbody[M.pA[ip]], bB = M.gbody[M.pB[ip]];
+        const double fn_c = Po.PG[6 * pst + is];
         V3 f_BC = {0, 0, 0};
         if (fn_c > 0.0) {
-          const V3 nhat = load_V(Po.PG, M.npp, ip), p_WC = load_V(Po.PG + 3 * M.npp, M.npp, ip);
+          const V3 nhat = load_V(Po.PG, pst, is), p_WC = load_V(Po.PG + 3 * pst, pst, is);
           V3 v_Ac = {0, 0, 0}, v_Bc = {0, 0, 0};
           if (bA >= 0) {
             const int gs = C.gslot[bA];
@@ -351,7 +409,7 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
           const V3 ft_BC = (sc.mu * fn) * that_regularized;
           f_BC = fn * nhat + ft_BC;
         }
-        store_V(S.PF, M.npp, ip, f_BC);
+        store_V(S.PF, pst, is, f_BC);
       }
     }
     __syncwarp();
@@ -367,12 +425,14 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
       const V3 p_WB = load_V(S.P, nb, b);
       if (kBias && C.gslot[b] >= 0) {  // contact forces on this body in pair order (cc:376-384)
         V3 Ft = {0, 0, 0}, Ff = {0, 0, 0};
-        for (int ip = 0; ip < M.np; ++ip)
-          if (Po.PG[6 * M.npp + ip] > 0.0) {
+        const int nslot = C.prune ? min(int(ids[pst]), pst) : M.np;
+        for (int is = 0; is < nslot; ++is)
+          if (Po.PG[6 * pst + is] > 0.0) {
+            const int ip = C.prune ? slot_pair(ids, is, M.np) : is;
             const int bA = M.gbody[M.pA[ip]], bB = M.gbody[M.pB[ip]];
             if (bA == b || bB == b) {
-              const V3 f = load_V(S.PF, M.npp, ip);
-              const V3 pc = load_V(Po.PG + 3 * M.npp, M.npp, ip) - p_WB;
+              const V3 f = load_V(S.PF, pst, is);
+              const V3 pc = load_V(Po.PG + 3 * pst, pst, is) - p_WB;
               if (bA == b) Ft = Ft + cross(pc, -f), Ff = Ff - f;
               if (bB == b) Ft = Ft + cross(pc, f), Ff = Ff + f;
             }

@@ -15,6 +15,7 @@ namespace {
 
 struct ChainLayout {
   int slots, groups, threads, smem_bytes;
+  int nsplit, ncolc;  // the columns of a (b,t) slot are dealt to nsplit CTAs, ncolc columns each
 };
 
 // shared memory: tables | per slot 2 shared poses | per group: eval scratch + private pose + 3 tau rows
@@ -23,28 +24,40 @@ __host__ __device__ inline int cgroup_doubles(const DevModel& dm, int nv, int nt
   const int n = ceval_doubles(dm) + cpose_private_doubles(dm) + ntau * nv;
   return n + ((dm.cg_res - n) & 15);  // groups of one warp must not start in the same bank
 }
+inline int chain_smem_bytes(const DevModel& dm, int nv, int ntau, int slots, int ncolc) {
+  return model_smem_bytes(dm) + 8 * nv +
+         8 * ((slots + 1) * 2 * cpose_doubles(dm) + (slots * ncolc + 1) * cgroup_doubles(dm, nv, ntau));
+}
 
 // Padding groups (thread count rounded up to a warp) share one dummy area, so shared memory is sized by
-// the groups that do real work: slots * nq + 1.
-ChainLayout chain_layout(const DevModel& dm, int nq, int nv, int ntau) {
+// the groups that do real work: slots * ncolc + 1.  A model whose evaluations are too large for all the
+// columns of even one slot (allegro hand: 23 columns x 7.4 KB) splits the columns of a slot over several CTAs;
+// each of them computes the two shared poses of the slot for itself.
+ChainLayout chain_layout(const DevModel& dm, int ncol, int nv, int ntau) {
   ChainLayout L;
-  const int per_slot = nq * dm.cgroup;
-  const int budget = 226 * 1024 - model_smem_bytes(dm) - 8 * nv;
+  const int budget = 226 * 1024;
   static const int max_slots = [] {  // tuning knob; 3 slots measured fastest on the quadruped
     const char* e = std::getenv("IDTO_CHAIN_SLOTS");
     return e ? std::max(1, std::atoi(e)) : 64;
   }();
-  int best = 1;
-  for (int s = 1; s <= 64; ++s) {
-    const int threads = (s * per_slot + 31) / 32 * 32;
-    const int bytes = 8 * ((s + 1) * 2 * cpose_doubles(dm) + (s * nq + 1) * cgroup_doubles(dm, nv, ntau));
-    if (threads <= 320 && bytes <= budget && s <= max_slots) best = s;
+  for (int nsplit = 1; nsplit <= ncol; ++nsplit) {
+    const int ncolc = (ncol + nsplit - 1) / nsplit;
+    if (nsplit > 1 && (ncol + nsplit - 2) / (nsplit - 1) == ncolc) continue;  // same chunk size, more CTAs
+    const int per_slot = ncolc * dm.cgroup;
+    int best = 0;
+    for (int s = 1; s <= 64; ++s) {
+      const int threads = (s * per_slot + 31) / 32 * 32;
+      if (threads <= 320 && chain_smem_bytes(dm, nv, ntau, s, ncolc) <= budget && s <= max_slots) best = s;
+    }
+    if (best == 0 && ncolc > 1) continue;
+    if (best == 0) best = 1;  // (rejected at solver creation: chain_min_smem_bytes)
+    L.nsplit = nsplit, L.ncolc = ncolc;
+    L.slots = best;
+    L.threads = (best * per_slot + 31) / 32 * 32;
+    L.groups = best * ncolc + 1;
+    L.smem_bytes = chain_smem_bytes(dm, nv, ntau, best, ncolc);
+    break;
   }
-  L.slots = best;
-  L.threads = (best * per_slot + 31) / 32 * 32;
-  L.groups = best * nq + 1;
-  L.smem_bytes = model_smem_bytes(dm) + 8 * nv +
-                 8 * ((best + 1) * 2 * cpose_doubles(dm) + L.groups * cgroup_doubles(dm, nv, ntau));
   return L;
 }
 
@@ -52,17 +65,21 @@ ChainLayout chain_layout(const DevModel& dm, int nq, int nv, int ntau) {
 
 template <int CG, int NLEV, int METHOD>
 __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverConsts sc, SolverBufs bf, int slots,
-                                                           int force) {
+                                                           int nsplit, int force) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int T = sc.T, nq = sc.nq, nv = sc.nv;
   const int g = threadIdx.x / CG, c = threadIdx.x % CG;
-  const int ncol = dm.nfull;  // columns differentiated here (the path columns go to kernels_path.cu)
+  // columns differentiated here (the path columns go to kernels_path.cu): this CTA takes chunk `chunk` of
+  // ncol columns (nsplit == 1: all of them) for each of its slots
+  const int ncol = (dm.nfull + nsplit - 1) / nsplit, chunk = blockIdx.x % nsplit;
   const int slot = g / ncol, ii = g % ncol;
-  const int i = (dm.itab + dm.o_fullcols)[ii];
-  const int sg = blockIdx.x * slots + slot;
-  const bool valid = (slot < slots) && (sg < sc.B * T);
-  const int b = valid ? sg / T : 0;
-  const int t = valid ? sg % T + 1 : 1;
+  const int icol = chunk * ncol + ii;
+  const int i = (dm.itab + dm.o_fullcols)[icol < dm.nfull ? icol : dm.nfull - 1];
+  const int sg = (blockIdx.x / nsplit) * slots + slot;
+  const bool valid_slot = (slot < slots) && (sg < sc.B * T);
+  const bool valid = valid_slot && icol < dm.nfull;
+  const int b = valid_slot ? sg / T : 0;
+  const int t = valid_slot ? sg % T + 1 : 1;
   const bool live = valid && (force || bf.ctl[b].derivs_dirty);
   if (!__syncthreads_or(live ? 1 : 0)) return;
 
@@ -77,7 +94,7 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   base += nv;
   constexpr int NTAU = METHOD == IDTO_GRAD_CENTRAL4 ? 3 : 2;
   const int pd = cpose_doubles(dm), gd = cgroup_doubles(dm, nv, NTAU);
-  const int sslot = valid ? slot : slots;  // padding groups write their (discarded) poses to a dummy slot
+  const int sslot = valid_slot ? slot : slots;  // padding groups write their (discarded) poses to a dummy slot
   const PoseSmem PB = make_cpose(dm, base + size_t(sslot) * 2 * pd);
   const PoseSmem PC = make_cpose(dm, base + size_t(sslot) * 2 * pd + pd);
   const int gidx = slot < slots ? g : slots * ncol;  // padding groups share one dummy area
@@ -118,14 +135,16 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
 
   // ---- phase 0: shared poses of q_{t+1} (even groups) and q_{t+2} (odd groups), first warp(s) of a slot ----
   {
-    const bool mine = valid && ii < 2 * CG && ii < ncol;  // enough groups to fill the warp that holds groups 0, 1
+    // the warp(s) holding groups 0 and 1 of a slot; all their lanes run the evaluation (shuffles, ballots), the
+    // lanes of other groups redundantly for the pose their own parity selects.  One call site: the warp must
+    // stay converged inside chain_eval.
+    const bool mine = valid_slot && ii < 2;
     if (__any_sync(0xffffffffu, mine)) {
       Perturb none = pt;
       none.owner = -1;
-      if ((ii & 1) == 0 || ncol == 1)
-        chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PB, S, c, qB + size_t(tp1) * nq, vB, aB, none, T0);
-      else
-        chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PC, S, c, qB + size_t(tp2) * nq, vB, aB, none, T0);
+      const bool second = (ii & 1) != 0 && ncol != 1;
+      const PoseSmem P0 = second ? PC : PB;
+      chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, P0, S, c, qB + size_t(second ? tp2 : tp1) * nq, vB, aB, none, T0);
       if (ncol == 1) chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PC, S, c, qB + size_t(tp2) * nq, vB, aB, none, T0);
     }
   }
@@ -236,7 +255,7 @@ static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc,
   launch_partials_path(dm, sc, bf, force, stream);
   if (dm.nfull == 0) return;
   const ChainLayout L = chain_layout(dm, dm.nfull, sc.nv, sc.method == IDTO_GRAD_CENTRAL4 ? 3 : 2);
-  const int grid = (sc.B * sc.T + L.slots - 1) / L.slots;
+  const int grid = (sc.B * sc.T + L.slots - 1) / L.slots * L.nsplit;
   g_launch_counter += 1;
 #define IDTO_LAUNCH_PC(METHOD)                                                                                   \
   {                                                                                                              \
@@ -246,7 +265,8 @@ static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc,
                            227 * 1024);                                                                          \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    k_partials_chain<CG, NLEV, METHOD><<<grid, L.threads, L.smem_bytes, stream>>>(dm, sc, bf, L.slots, force);   \
+    k_partials_chain<CG, NLEV, METHOD><<<grid, L.threads, L.smem_bytes, stream>>>(dm, sc, bf, L.slots, L.nsplit,  \
+                                                                                  force);                        \
   }
   switch (sc.method) {
     case IDTO_GRAD_FORWARD: IDTO_LAUNCH_PC(IDTO_GRAD_FORWARD) break;
@@ -303,13 +323,12 @@ static int chain_key(const DevModel& dm) {
     default: break;                               \
   }
 
-// Shared memory one CTA of the ID kernels needs for this model (a single slot is the minimum): the contact-pair
-// scratch is sized by the number of CANDIDATE pairs, so models with hundreds of pairs (allegro hand: 187) do
-// not fit until the pair list is pruned per evaluation.
+// Shared memory one CTA of the ID kernels needs for this model (a single slot is the minimum).  The contact-pair
+// scratch is sized by dm.nact: every candidate pair for small models, kMaxActivePairs compacted slots for models
+// with more candidates than that (allegro hand: 188).
 int chain_min_smem_bytes(const DevModel& dm, int nv, int method) {
   const int ntau = method == IDTO_GRAD_CENTRAL4 ? 3 : 2;
-  const int ncol = dm.nfull > 0 ? dm.nfull : 1;
-  const int partials = model_smem_bytes(dm) + 8 * nv + 8 * (2 * 2 * cpose_doubles(dm) + (ncol + 1) * cgroup_doubles(dm, nv, ntau));
+  const int partials = chain_smem_bytes(dm, nv, ntau, 1, 1);  // one slot, one column per CTA
   const int tau = model_smem_bytes(dm) + (64 / dm.cgroup) * cgroup_doubles(dm, nv, 1) * 8;
   return partials > tau ? partials : tau;
 }

@@ -22,7 +22,11 @@ namespace idto {
 
 constexpr int kMaxChildren = 8;
 constexpr int kMaxGroup = 32;
-constexpr int kMaxLevels = 8;    // tree depth supported by the chain-lane kernels  // bodies per inverse-dynamics evaluation group (lanes)
+constexpr int kMaxLevels = 8;    // tree depth supported by the chain-lane kernels
+// Contact pairs one inverse-dynamics evaluation can have ACTIVE (signed distance <= threshold, cc:268-275) at the
+// same time when the model has more candidate pairs than this: each evaluation then compacts the active pairs,
+// in candidate order, into a list of this capacity (dynamics_chain.cuh) instead of keeping every candidate.
+constexpr int kMaxActivePairs = 32;
 
 // Baked model on the device: two SoA tables (ints, doubles) copied to shared memory by TMA.
 struct DevModel {
@@ -30,6 +34,7 @@ struct DevModel {
   const double* dtab;
   int itab_bytes, dtab_bytes;  // multiples of 16
   int nb, nbp, nq, nv, ng, np, npp, nlevels, group;  // nbp/npp: padded strides; group: lanes per evaluation
+  int nact, prune;  // per-evaluation pair slots (npp, or kMaxActivePairs when np is larger: prune = 1)
   // chain decomposition (lane = kinematic chain, step = tree level): cgroup lanes per evaluation
   int cgroup, nchains, ngb, ngd;  // ngb: bodies carrying geometry, ngd: geometries on moving bodies
   int chain_ok;                   // the chain-lane kernels support this model
@@ -59,6 +64,7 @@ struct SolverConsts {
   const int* unact;                       // device [nu]
   const int* quat_starts;                 // device [nquat]
   int nquat;
+  int* status;                            // == SolverBufs::status (sticky error flag), for device functions
 };
 
 // One TrajectoryOptimizerState's trajectory-level cache (state.h:37-351) for the batch.
@@ -96,7 +102,7 @@ struct SolverBufs {
   ProbCtl* ctl;
   double* stats;  // [B][stats_cap][IDTO_NUM_STATS]
   int stats_cap;
-  int* status;  // [1] sticky device-side error flag (factorisation failure)
+  int* status;  // [1] sticky device-side error flag (factorisation failure, active-pair overflow)
 };
 
 // ---- kernel launchers (each in its own .cu; all asynchronous on `stream`) ---------------------
