@@ -174,6 +174,7 @@ void make_view(const idto_solver_s* s, int b0, int nb, SolverConsts* scv, Solver
   for (TrajBuf* tb : {&v.st, &v.sc}) {
     tb->q += o * T1 * nq, tb->v += o * T1 * nv, tb->a += o * T * nv, tb->tau += o * T * nv;
     tb->Nplus += o * T1 * nv * nq, tb->cost += o, tb->h += o * nh;
+    if (tb->near) tb->near += o * T * kNearStride;
   }
   v.q_init += o * nq, v.v_init += o * nv, v.q_nom += o * T1 * nq, v.v_nom += o * T1 * nv;
   v.dqm += o * T * nv * nq, v.dqt += o * T * nv * nq, v.dqp += o * T * nv * nq;
@@ -415,6 +416,18 @@ int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
   dm.nb = nb, dm.nbp = nbp, dm.nq = d->nq, dm.nv = d->nv, dm.ng = ngp, dm.np = np, dm.npp = npp;
   dm.prune = np > kMaxActivePairs ? 1 : 0;
   dm.nact = dm.prune ? kMaxActivePairs : npp;
+  {
+    double chain = 0.0, off = 0.0;
+    for (int k = 0; k < nb; ++k) {
+      const double* p = d->X_PF + size_t(k) * 12 + 9;
+      chain += std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    }
+    for (int gi = 0; gi < ng; ++gi) {
+      const double* p = d->X_BG + size_t(gi) * 12 + 9;
+      off = std::max(off, std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
+    }
+    dm.reach = chain + off;
+  }
   dm.nlevels = nlevels, dm.group = G;
   dm.gx = d->gravity[0], dm.gy = d->gravity[1], dm.gz = d->gravity[2];
   std::vector<int> parent_p(nbp, -1);
@@ -652,6 +665,8 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   for (TrajBuf* tb : {&bf.st, &bf.sc}) {
     alloc(&tb->q, nTq), alloc(&tb->v, nTv), alloc(&tb->a, nA), alloc(&tb->tau, nA), alloc(&tb->Nplus, nN);
     alloc(&tb->cost, B), alloc(&tb->h, size_t(B) * nh);
+    tb->near = nullptr;
+    if (m->dm.prune) ok = ok && A.get(&tb->near, size_t(B) * T * kNearStride) == cudaSuccess;
   }
   alloc(&s->q_init, size_t(B) * nq), alloc(&s->v_init, size_t(B) * nv), alloc(&s->q_nom, nTq), alloc(&s->v_nom, nTv);
   alloc(&bf.dqm, nP), alloc(&bf.dqt, nP), alloc(&bf.dqp, nP);

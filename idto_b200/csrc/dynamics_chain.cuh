@@ -143,6 +143,14 @@ struct Perturb {
 
 enum { kEvalFull = 0, kEvalSharedPose = 1, kEvalSharedPoseNoBias = 2, kEvalPoseOnly = 3 };
 
+// How one evaluation visits the contact pairs (all fields group-uniform; near_in == nullptr must be warp-uniform).
+struct PairWalk {
+  const int* near_in = nullptr;  // pruned models: walk this near list instead of every candidate
+  int* near_out = nullptr;       // pruned models: write the near list of this (unperturbed) pose
+  double margin = 0.0;           // near_out: distance <= threshold + margin
+  bool skip = false;             // no contact geometry wanted (pose used by bias-free evaluations only)
+};
+
 // One inverse-dynamics evaluation by a group of CG lanes (all 32 lanes of the warp must call).
 //   MODE kEvalFull:           pose from q (written to `Po`), velocities, forces -> tau
 //   MODE kEvalSharedPose:     pose read from `Po` (computed earlier), velocities, forces -> tau
@@ -161,7 +169,8 @@ template <int CG, int NLEV, int MODE, bool STASH = false>
 __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& sc, const PoseSmem& Po,
                                            const EvalSmem& S, int c, const double* __restrict__ q,
                                            const double* __restrict__ v, const double* __restrict__ a,
-                                           const Perturb& pt, double* tau_out, double* stash = nullptr) {
+                                           const Perturb& pt, double* tau_out, double* stash = nullptr,
+                                           const PairWalk pw = PairWalk()) {
   const SModel& M = C.M;
   const int nb = M.nb;
   const int gbase = (threadIdx.x & 31) / CG * CG;
@@ -343,31 +352,42 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
   if ((kPose || kBias) && M.np > 0) {
     if (kPose) {
       if (C.prune) {
-        int count = 0;
-        for (int ip0 = 0; ip0 < M.np; ip0 += CG) {
-          const int ip = ip0 + c;
+        // candidates of this evaluation: the near list of the unperturbed pose, or all of them
+        const bool walk_near = pw.near_in != nullptr;
+        const int ncand = pw.skip ? 0 : (walk_near ? min(max(pw.near_in[0], 0), kMaxActivePairs) : M.np);
+        const int nmax = __reduce_max_sync(0xffffffffu, ncand);  // the ballots need a warp-uniform trip count
+        const unsigned gmask = CG == 32 ? 0xffffffffu : ((1u << (CG & 31)) - 1u), below = (1u << c) - 1u;
+        int count = 0, ncount = 0;
+        for (int k0 = 0; k0 < nmax; k0 += CG) {
+          const int k = k0 + c;
+          int ip = -1;
+          if (k < ncand) ip = walk_near ? min(max(pw.near_in[1 + k], 0), M.np - 1) : k;
           PairGeom pg;
-          bool act = false;
-          if (ip < M.np) {
+          bool act = false, nearby = false;
+          if (ip >= 0) {
             pg = pair_geometry(C, Po, ip);
             act = pg.distance <= sc.threshold;
+            nearby = pg.distance <= sc.threshold + pw.margin;
           }
-          const unsigned grp = (__ballot_sync(0xffffffffu, act) >> gbase) & (CG == 32 ? 0xffffffffu : ((1u << (CG & 31)) - 1u));
-          const int pos = count + __popc(grp & ((1u << c) - 1u));
+          const unsigned grp = (__ballot_sync(0xffffffffu, act) >> gbase) & gmask;
+          const unsigned ngrp = (__ballot_sync(0xffffffffu, nearby) >> gbase) & gmask;
+          const int pos = count + __popc(grp & below), npos = ncount + __popc(ngrp & below);
           if (act && pos < pst) {
             store_V(Po.PG, pst, pos, pg.nhat);
             store_V(Po.PG + 3 * pst, pst, pos, pg.p_WC);
             Po.PG[6 * pst + pos] = contact_fn_c(sc, pg.distance);
             ids[pos] = double(ip);
           }
-          count += __popc(grp);
+          if (nearby && pw.near_out && npos < kMaxActivePairs) pw.near_out[1 + npos] = ip;
+          count += __popc(grp), ncount += __popc(ngrp);
         }
         if (c == 0) {
           ids[pst] = double(count < pst ? count : pst);
-          if (count > pst) atomicExch(sc.status, IDTO_ERR_CONTACT_OVERFLOW);
+          if (pw.near_out) pw.near_out[0] = ncount < kMaxActivePairs ? ncount : kMaxActivePairs;
+          if (count > pst || (pw.near_out && ncount > kMaxActivePairs)) atomicExch(sc.status, IDTO_ERR_CONTACT_OVERFLOW);
         }
         __syncwarp();
-      } else {
+      } else if (!pw.skip) {
         for (int ip = c; ip < M.np; ip += CG) {
           const PairGeom pg = pair_geometry(C, Po, ip);
           store_V(Po.PG, pst, ip, pg.nhat);

@@ -24,9 +24,12 @@ __host__ __device__ inline int cgroup_doubles(const DevModel& dm, int nv, int nt
   const int n = ceval_doubles(dm) + cpose_private_doubles(dm) + ntau * nv;
   return n + ((dm.cg_res - n) & 15);  // groups of one warp must not start in the same bank
 }
+// Padding groups write the shared poses they compute to a dummy slot — except for pruned models (large poses,
+// shared memory is what limits them), whose padding groups shadow slot 0 of the CTA instead (same values).
+__host__ __device__ inline int dummy_pose_slots(const DevModel& dm) { return dm.prune ? 0 : 1; }
 inline int chain_smem_bytes(const DevModel& dm, int nv, int ntau, int slots, int ncolc) {
   return model_smem_bytes(dm) + 8 * nv +
-         8 * ((slots + 1) * 2 * cpose_doubles(dm) + (slots * ncolc + 1) * cgroup_doubles(dm, nv, ntau));
+         8 * ((slots + dummy_pose_slots(dm)) * 2 * cpose_doubles(dm) + (slots * ncolc + 1) * cgroup_doubles(dm, nv, ntau));
 }
 
 // Padding groups (thread count rounded up to a warp) share one dummy area, so shared memory is sized by
@@ -40,9 +43,13 @@ ChainLayout chain_layout(const DevModel& dm, int ncol, int nv, int ntau) {
     const char* e = std::getenv("IDTO_CHAIN_SLOTS");
     return e ? std::max(1, std::atoi(e)) : 64;
   }();
-  for (int nsplit = 1; nsplit <= ncol; ++nsplit) {
+  static const int min_split = [] {  // tuning knob: at least this many CTAs per slot
+    const char* e = std::getenv("IDTO_CHAIN_NSPLIT");
+    return e ? std::max(1, std::atoi(e)) : 1;
+  }();
+  for (int nsplit = std::min(min_split, ncol); nsplit <= ncol; ++nsplit) {
     const int ncolc = (ncol + nsplit - 1) / nsplit;
-    if (nsplit > 1 && (ncol + nsplit - 2) / (nsplit - 1) == ncolc) continue;  // same chunk size, more CTAs
+    if (nsplit > min_split && (ncol + nsplit - 2) / (nsplit - 1) == ncolc) continue;  // same chunk size, more CTAs
     const int per_slot = ncolc * dm.cgroup;
     int best = 0;
     for (int s = 1; s <= 64; ++s) {
@@ -78,8 +85,9 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   const int sg = (blockIdx.x / nsplit) * slots + slot;
   const bool valid_slot = (slot < slots) && (sg < sc.B * T);
   const bool valid = valid_slot && icol < dm.nfull;
-  const int b = valid_slot ? sg / T : 0;
-  const int t = valid_slot ? sg % T + 1 : 1;
+  const int sgx = valid_slot ? sg : (blockIdx.x / nsplit) * slots;  // padding groups shadow the CTA's first slot
+  const int b = sgx / T;
+  const int t = sgx % T + 1;
   const bool live = valid && (force || bf.ctl[b].derivs_dirty);
   if (!__syncthreads_or(live ? 1 : 0)) return;
 
@@ -94,11 +102,12 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   base += nv;
   constexpr int NTAU = METHOD == IDTO_GRAD_CENTRAL4 ? 3 : 2;
   const int pd = cpose_doubles(dm), gd = cgroup_doubles(dm, nv, NTAU);
-  const int sslot = valid_slot ? slot : slots;  // padding groups write their (discarded) poses to a dummy slot
+  // padding groups write their (discarded) poses to a dummy slot, or (same values) to the slot they shadow
+  const int sslot = valid_slot ? slot : (dummy_pose_slots(dm) ? slots : 0);
   const PoseSmem PB = make_cpose(dm, base + size_t(sslot) * 2 * pd);
   const PoseSmem PC = make_cpose(dm, base + size_t(sslot) * 2 * pd + pd);
   const int gidx = slot < slots ? g : slots * ncol;  // padding groups share one dummy area
-  double* gbase = base + size_t(slots + 1) * 2 * pd + size_t(gidx) * gd;
+  double* gbase = base + size_t(slots + dummy_pose_slots(dm)) * 2 * pd + size_t(gidx) * gd;
   const EvalSmem S = make_ceval(dm, gbase);
   const PoseSmem PA = make_cpose_private(dm, gbase + ceval_doubles(dm));
   double* T0 = gbase + ceval_doubles(dm) + cpose_private_doubles(dm);
@@ -109,6 +118,8 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   const double* vB = bf.st.v + size_t(b) * (T + 1) * nv;
   const double* aB = bf.st.a + size_t(b) * T * nv;
   const int tp1 = t < T ? t + 1 : t, tp2 = t < T - 1 ? t + 2 : t;  // clamped rows for predicated-off work
+  // pruned models: near lists of the unperturbed poses of this problem, entry j for q_{j+1} (k_tau_chain)
+  const int* near_list = dm.prune ? bf.st.near + size_t(b) * T * kNearStride : nullptr;
 
   // ---- column bookkeeping (every lane computes it: no shuffles needed) ------------------------------------
   const int owner = C.M.qowner[i];
@@ -144,8 +155,15 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
       none.owner = -1;
       const bool second = (ii & 1) != 0 && ncol != 1;
       const PoseSmem P0 = second ? PC : PB;
-      chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, P0, S, c, qB + size_t(second ? tp2 : tp1) * nq, vB, aB, none, T0);
-      if (ncol == 1) chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PC, S, c, qB + size_t(tp2) * nq, vB, aB, none, T0);
+      // the pose of q_{t+2} only serves the bias-free evaluations of phase C: no contact geometry
+      PairWalk pw;
+      pw.near_in = near_list ? near_list + size_t(tp1 - 1) * kNearStride : nullptr;
+      pw.skip = second;
+      chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, P0, S, c, qB + size_t(second ? tp2 : tp1) * nq, vB, aB, none, T0,
+                                          nullptr, pw);
+      pw.skip = true;
+      if (ncol == 1)
+        chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PC, S, c, qB + size_t(tp2) * nq, vB, aB, none, T0, nullptr, pw);
     }
   }
 
@@ -173,12 +191,14 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   };
 
   // ---- A: tau[t-1] = ID(q_t^e, v_t^e, a_{t-1}^e)   (cc:526-531, 763-787) --------------------------------
+  PairWalk pwA;  // the perturbed pose can only activate pairs of the near list of q_t
+  pwA.near_in = near_list ? near_list + size_t(t - 1) * kNearStride : nullptr;
 #pragma unroll 1
   for (int kk = 0; kk < NK; ++kk) {
     const double m = ((kk & 1) ? -1.0 : 1.0) * ((kk >= 2) ? 2.0 : 1.0);
     pt.dq = m * dq, pt.cv = m * dv, pt.ca = m * da, pt.uv = 1.0, pt.ua = 1.0, pt.nv3 = nt3, pt.na3 = nt3;
     chain_eval<CG, NLEV, kEvalFull>(C, sc, PA, S, c, qB + size_t(t) * nq, vB + size_t(t) * nv,
-                                    aB + size_t(t - 1) * nv, pt, (kk & 1) ? T1 : T0);
+                                    aB + size_t(t - 1) * nv, pt, (kk & 1) ? T1 : T0, nullptr, pwA);
     if (METHOD == IDTO_GRAD_CENTRAL4 && kk == 1) stash_d1();
   }
   emit(bf.dqp + (size_t(b) * T + (t - 1)) * nv * nq, bf.st.tau + (size_t(b) * T + (t - 1)) * nv, true);
@@ -237,9 +257,19 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
   none.dq = none.cv = none.ca = 0.0, none.uv = none.ua = 1.0, none.nv3 = none.na3 = {0, 0, 0};
   // (groups that are not live write their records to the slot of item (0, 0): same values as its owner)
   double* rec = STASH ? stash + (size_t(live ? b : 0) * T + (live ? t : 0)) * dm.nb * kStashDoubles : nullptr;
-  chain_eval<CG, NLEV, kEvalFull, STASH>(C, sc, PA, S, c, tb.q + (size_t(live ? b : 0) * (T + 1) + (live ? t : 0) + 1) * nq,
+  const double* qrow = tb.q + (size_t(live ? b : 0) * (T + 1) + (live ? t : 0) + 1) * nq;
+  PairWalk pw;
+  if (dm.prune && !STASH && tb.near && live) {
+    // what a finite-difference perturbation of one coordinate (|dq| <= 2 sqrt(eps) max(1,|q_i|), cc:506, 763) can
+    // move a geometry centre by: |dq| times a lever arm bounded by the chain lengths plus the joint travel
+    double qmax = 1.0;
+    for (int e = 0; e < nq; ++e) qmax = fmax(qmax, fabs(qrow[e]));
+    pw.near_out = tb.near + (size_t(b) * T + t) * kNearStride;
+    pw.margin = 4e-7 * qmax * (dm.reach + dm.nb * qmax);
+  }
+  chain_eval<CG, NLEV, kEvalFull, STASH>(C, sc, PA, S, c, qrow,
                                          tb.v + (size_t(live ? b : 0) * (T + 1) + (live ? t : 0) + 1) * nv,
-                                         tb.a + (size_t(live ? b : 0) * T + (live ? t : 0)) * nv, none, T0, rec);
+                                         tb.a + (size_t(live ? b : 0) * T + (live ? t : 0)) * nv, none, T0, rec, pw);
   __syncwarp();
   if (live && !STASH) {
     double* tau = tb.tau + (size_t(b) * T + t) * nv;

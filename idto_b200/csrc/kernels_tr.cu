@@ -327,6 +327,9 @@ __global__ void __launch_bounds__(kRowThreads) k_trust_update(SolverConsts sc, S
       bf.st.Nplus[o] = bf.sc.Nplus[o];
     }
     for (int e = tid; e < nh; e += nt) bf.st.h[size_t(b) * nh + e] = bf.sc.h[size_t(b) * nh + e];
+    if (bf.st.near)  // near lists of the adopted poses (pruned contact models)
+      for (int e = tid; e < T * kNearStride; e += nt)
+        bf.st.near[size_t(b) * T * kNearStride + e] = bf.sc.near[size_t(b) * T * kNearStride + e];
   }
   // Convergence (cc:2601-2611) needs EvalMeritFunctionGradient of the NEW state, i.e. the
   // derivative pipeline of the next iteration: it is marked pending here and evaluated by

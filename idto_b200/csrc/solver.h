@@ -27,6 +27,11 @@ constexpr int kMaxLevels = 8;    // tree depth supported by the chain-lane kerne
 // same time when the model has more candidate pairs than this: each evaluation then compacts the active pairs,
 // in candidate order, into a list of this capacity (dynamics_chain.cuh) instead of keeping every candidate.
 constexpr int kMaxActivePairs = 32;
+// Near list of a pose (pruned models): [0] count, [1..] candidate indices, ascending, of the pairs whose signed
+// distance at the UNPERTURBED pose is within the activation distance plus a margin that bounds what a finite-
+// difference perturbation can move (k_tau_chain writes it while it walks every candidate anyway; the perturbed
+// evaluations of the ID partials walk it instead of the candidates).
+constexpr int kNearStride = kMaxActivePairs + 1;
 
 // Baked model on the device: two SoA tables (ints, doubles) copied to shared memory by TMA.
 struct DevModel {
@@ -35,6 +40,7 @@ struct DevModel {
   int itab_bytes, dtab_bytes;  // multiples of 16
   int nb, nbp, nq, nv, ng, np, npp, nlevels, group;  // nbp/npp: padded strides; group: lanes per evaluation
   int nact, prune;  // per-evaluation pair slots (npp, or kMaxActivePairs when np is larger: prune = 1)
+  double reach;     // bound on the lever arm of any joint on any geometry centre at q = 0 (near-list margin)
   // chain decomposition (lane = kinematic chain, step = tree level): cgroup lanes per evaluation
   int cgroup, nchains, ngb, ngd;  // ngb: bodies carrying geometry, ngd: geometries on moving bodies
   int chain_ok;                   // the chain-lane kernels support this model
@@ -70,6 +76,7 @@ struct SolverConsts {
 // One TrajectoryOptimizerState's trajectory-level cache (state.h:37-351) for the batch.
 struct TrajBuf {
   double *q, *v, *a, *tau, *Nplus, *cost, *h;
+  int* near;  // [B][T][kNearStride] near list of pose q_{t+1} (pruned models only, else null)
 };
 
 // Per-problem trust-region control block (device resident; host never reads it mid-solve).

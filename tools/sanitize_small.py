@@ -8,7 +8,8 @@ from idto_b200 import capi, problems
 from idto_b200.types import GRAD_CENTRAL, GRAD_FORWARD
 
 for name, T, method, B in (("hopper", 9, GRAD_CENTRAL, 2), ("mini_cheetah", 8, GRAD_CENTRAL, 2),
-                           ("spinner", 8, GRAD_FORWARD, 1)):
+                           ("spinner", 8, GRAD_FORWARD, 1), ("allegro_hand", 6, GRAD_FORWARD, 2),
+                           ("allegro_hand", 5, GRAD_CENTRAL, 1)):
     m, dt, prob, params, guess = getattr(problems, name)(T=T, gradients_method=method)
     params.max_iterations = 2
     gs = capi.BatchSolver(capi.Model(m), dt, prob, params, B)
