@@ -32,8 +32,9 @@ from dataclasses import dataclass, field
 import numpy as np
 
 JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_PLANAR, JOINT_QUAT_FLOATING = 0, 1, 2, 3
-GEOM_SPHERE, GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER = 0, 1, 2, 3
-_GEOM_CODE = {"sphere": GEOM_SPHERE, "box": GEOM_BOX, "capsule": GEOM_CAPSULE, "cylinder": GEOM_CYLINDER}
+GEOM_SPHERE, GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_HALF_SPACE = 0, 1, 2, 3, 4
+_GEOM_CODE = {"sphere": GEOM_SPHERE, "box": GEOM_BOX, "capsule": GEOM_CAPSULE, "cylinder": GEOM_CYLINDER,
+              "half_space": GEOM_HALF_SPACE}
 _JOINT_NQ = {JOINT_REVOLUTE: 1, JOINT_PRISMATIC: 1, JOINT_PLANAR: 3, JOINT_QUAT_FLOATING: 7}
 _JOINT_NV = {JOINT_REVOLUTE: 1, JOINT_PRISMATIC: 1, JOINT_PLANAR: 3, JOINT_QUAT_FLOATING: 6}
 
@@ -463,6 +464,16 @@ class ModelBuilder:
         self._next_geom += 1
         return self
 
+    @staticmethod
+    def half_space_pose(normal, point):
+        """HalfSpace::MakePose(Hz_dir_F, p_FB) analogue: a frame whose z axis is `normal` and whose origin is
+        `point` (any completion of the basis describes the same half space)."""
+        z = np.asarray(normal, float) / np.linalg.norm(normal)
+        a = np.eye(3)[int(np.argmin(np.abs(z)))]
+        x = np.cross(a, z)
+        x /= np.linalg.norm(x)
+        return X(np.column_stack([x, np.cross(z, x), z]), np.asarray(point, float))
+
     # -- finalize -------------------------------------------------------------
     def finalize(self) -> BakedModel:
         child_joint = {j.child: j for j in self.joints}
@@ -565,7 +576,7 @@ class ModelBuilder:
         for g in geoms:
             if g[2] not in _GEOM_CODE:
                 raise NotImplementedError(
-                    f"collision shape {g[2]!r} on link {g[6]!r}: only sphere/box/capsule/cylinder have "
+                    f"collision shape {g[2]!r} on link {g[6]!r}: only sphere/box/capsule/cylinder/half_space have "
                     "closed-form signed distance here (SURVEY.md §7 'hard parts')")
         # default collision filtering
         def body_parent(bi):
@@ -671,6 +682,12 @@ def bake_reference_models(reference_root="/root/reference", out_dir=_MODEL_DIR):
     b = ModelBuilder().add_urdf(os.path.join(mdl, "hopper.urdf"))
     b.register_collision_geometry("world", X(p=[0.0, 0.0, -5.0]), "box", [25.0, 25.0, 10.0], "ground")
     out["hopper"] = b.finalize()
+    # the same ground as a HalfSpace (plant.RegisterCollisionGeometry(world_body, HalfSpace::MakePose(z, 0),
+    # HalfSpace(), ...), the usual Drake ground): identical contact wherever the foot is over the box's top face
+    b = ModelBuilder().add_urdf(os.path.join(mdl, "hopper.urdf"))
+    b.register_collision_geometry("world", ModelBuilder.half_space_pose([0.0, 0.0, 1.0], [0.0, 0.0, 0.0]),
+                                  "half_space", [], "ground")
+    out["hopper_half_space"] = b.finalize()
     out["mini_cheetah"] = ModelBuilder().add_urdf(os.path.join(mdl, "mini_cheetah_with_ground.urdf")).finalize()
     # examples/allegro_hand/allegro_hand.cc:83-113: hand welded to the world with RPY(0, -pi/2, 0), free ball
     # (m = 0.05 kg, r = 0.06 m, solid sphere) with one collision sphere, registered after the hand's geometries

@@ -369,8 +369,8 @@ int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
   }
   const int nb = d->nbodies, ng = d->ngeoms, np = d->npairs;
   for (int i = 0; i < ng; ++i)
-    if (d->geom_type[i] < IDTO_GEOM_SPHERE || d->geom_type[i] > IDTO_GEOM_CYLINDER) {
-      set_last_error("unknown geometry type (sphere, box, capsule, cylinder are supported)");
+    if (d->geom_type[i] < IDTO_GEOM_SPHERE || d->geom_type[i] > IDTO_GEOM_HALF_SPACE) {
+      set_last_error("unknown geometry type (sphere, box, capsule, cylinder, half space are supported)");
       return IDTO_ERR_UNSUPPORTED;
     }
   for (int i = 0; i < np; ++i)

@@ -182,12 +182,19 @@ __device__ __forceinline__ PointDist point_to_cylinder(double r, double L, const
   const V3 p_WN = mul(R_WG, p_GN) + p_WG;
   return {dot(grad_W, p_WQ - p_WN), p_GN, grad_W};
 }
+// Half space z <= 0 of frame G: the height above the boundary plane; the witness point is the foot of the
+// perpendicular, the gradient the plane normal Gz in W.
+__device__ __forceinline__ PointDist point_to_half_space(const M3& R_WG, V3 p_WG, V3 p_WQ) {
+  const V3 p = tmul(R_WG, p_WQ - p_WG);
+  return {p.z, V3{p.x, p.y, 0.0}, V3{R_WG.m[2], R_WG.m[5], R_WG.m[8]}};
+}
 // Signed distance from the query point to the shape `type` (dims as in idto_model_desc::geom_dims).
 __device__ __forceinline__ PointDist point_to_shape(int type, V3 dims, const M3& R_WG, V3 p_WG, V3 p_WQ) {
   switch (type) {
     case IDTO_GEOM_SPHERE: return point_to_sphere(dims.x, R_WG, p_WG, p_WQ);
     case IDTO_GEOM_CAPSULE: return point_to_capsule(dims.x, dims.y, R_WG, p_WG, p_WQ);
     case IDTO_GEOM_CYLINDER: return point_to_cylinder(dims.x, dims.y, R_WG, p_WG, p_WQ);
+    case IDTO_GEOM_HALF_SPACE: return point_to_half_space(R_WG, p_WG, p_WQ);
     default: return point_to_box(dims, R_WG, p_WG, p_WQ);
   }
 }

@@ -83,8 +83,8 @@ def spinner_capsule(T=40, gradients_method=GRAD_FORWARD, max_iterations=200):
     return m, 0.05, prob, params, guess
 
 
-def hopper(T=50, gradients_method=GRAD_FORWARD, max_iterations=200):
-    m = load_model("hopper")
+def hopper(T=50, gradients_method=GRAD_FORWARD, max_iterations=200, model="hopper"):
+    m = load_model(model)  # "hopper_half_space": the same ground registered as a HalfSpace
     q0 = [0.61, 0.0, 0.3, -0.5, 0.2]
     qe = [0.61, -0.5, 0.3, -0.5, 0.2]
     prob = _make(m, T, 0.05, q0, [0] * 5, q0, qe, [1.0] * 5, [0.1] * 5, [1e2, 1e2, 1e2, 0.1, 0.1],

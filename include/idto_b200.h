@@ -42,8 +42,10 @@ enum {
  */
 enum { IDTO_JOINT_REVOLUTE = 0, IDTO_JOINT_PRISMATIC = 1, IDTO_JOINT_PLANAR = 2,
        IDTO_JOINT_QUAT_FLOATING = 3 };
-/* geom_dims: sphere (radius, -, -); box (full sizes x, y, z); capsule / cylinder (radius, length, -), axis = Gz */
-enum { IDTO_GEOM_SPHERE = 0, IDTO_GEOM_BOX = 1, IDTO_GEOM_CAPSULE = 2, IDTO_GEOM_CYLINDER = 3 };
+/* geom_dims: sphere (radius, -, -); box (full sizes x, y, z); capsule / cylinder (radius, length, -), axis = Gz;
+ * half space (-, -, -): the region z <= 0 of its frame G, outward normal +Gz (drake::geometry::HalfSpace) */
+enum { IDTO_GEOM_SPHERE = 0, IDTO_GEOM_BOX = 1, IDTO_GEOM_CAPSULE = 2, IDTO_GEOM_CYLINDER = 3,
+       IDTO_GEOM_HALF_SPACE = 4 };
 
 typedef struct {
   int nbodies, nq, nv;

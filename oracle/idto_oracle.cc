@@ -278,12 +278,21 @@ inline PointDist point_to_cylinder(double r, double L, const M3& R_WG, V3 p_WG, 
   return {dot(grad_W, p_WQ - p_WN), p_GN, grad_W};
 }
 
+// drake::geometry::HalfSpace: the region z <= 0 of its frame, so the signed distance is the z coordinate of the
+// query point in G, the nearest point its projection onto the plane z = 0, the gradient the normal Gz.
+inline PointDist point_to_half_space(const M3& R_WG, V3 p_WG, V3 p_WQ) {
+  const V3 p = tmul(R_WG, p_WQ - p_WG);
+  const V3 normal_W = R_WG * V3{0.0, 0.0, 1.0};
+  return {p.z, V3{p.x, p.y, 0.0}, normal_W};
+}
+
 // Signed distance from the query point to the shape `type` (dims as in idto_model_desc::geom_dims).
 inline PointDist point_to_shape(int type, V3 dims, const M3& R_WG, V3 p_WG, V3 p_WQ) {
   switch (type) {
     case IDTO_GEOM_SPHERE: return point_to_sphere(dims.x, R_WG, p_WG, p_WQ);
     case IDTO_GEOM_CAPSULE: return point_to_capsule(dims.x, dims.y, R_WG, p_WG, p_WQ);
     case IDTO_GEOM_CYLINDER: return point_to_cylinder(dims.x, dims.y, R_WG, p_WG, p_WQ);
+    case IDTO_GEOM_HALF_SPACE: return point_to_half_space(R_WG, p_WG, p_WQ);
     default: return point_to_box(dims, R_WG, p_WG, p_WQ);
   }
 }

@@ -1,12 +1,12 @@
 """Closed-form signed distances (Drake point_distance::DistanceToPoint restated in oracle/idto_oracle.cc and in
-idto_b200/csrc/dynamics.cuh): sphere, box, capsule, cylinder.  No numeric anchor for these exists in the
+idto_b200/csrc/dynamics.cuh): sphere, box, capsule, cylinder, half space.  No numeric anchor for these exists in the
 reference tree (parity unpinned at the Drake boundary); they are pinned here by brute force — the distance to a
 dense sampling of the surface — and by the properties of a signed distance field (|grad| = 1, the witness point
 lies on the surface along the gradient)."""
 import numpy as np
 import pytest
 
-from idto_b200.bake import GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_SPHERE
+from idto_b200.bake import GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_HALF_SPACE, GEOM_SPHERE
 
 
 def _rot(rng):
@@ -77,6 +77,54 @@ def test_point_distance_against_brute_force(oracle_mod, gtype, dims):
         assert np.min(np.linalg.norm(S - p_GN, axis=1)) < 2e-2  # the witness point is on the surface
         # moving from the witness point along the gradient by the signed distance reaches the query point
         assert np.allclose(R @ p_GN + p_WG + d * grad_W, p_WQ, atol=1e-12)
+
+
+def test_half_space_distance(oracle_mod):
+    """drake::geometry::HalfSpace: the region z <= 0 of its frame; signed distance = height above the plane."""
+    rng = np.random.default_rng(4)
+    for _ in range(40):
+        R, p_WG, p_G = _rot(rng), rng.normal(size=3), rng.uniform(-2, 2, 3)
+        d, p_GN, grad_W = oracle_mod.point_distance(GEOM_HALF_SPACE, [0, 0, 0], R, p_WG, R @ p_G + p_WG)
+        assert abs(d - p_G[2]) < 1e-14 and np.allclose(p_GN, [p_G[0], p_G[1], 0.0], atol=1e-14)
+        assert np.array_equal(grad_W, R[:, 2])
+
+
+def test_half_space_ground_equals_box_ground_over_the_box(oracle_mod):
+    """hopper_half_space.json: the hopper example's ground (a 25 x 25 x 10 box whose top face is z = 0,
+    examples/hopper/hopper.cc:44-50) registered as a HalfSpace instead.  Over the top face both report the same
+    distance, normal and witness point, so the whole pipeline agrees."""
+    from idto_b200 import problems
+    ma, dt, prob, params, guess = problems.hopper(T=12)
+    mb = problems.hopper(T=12, model="hopper_half_space")[0]
+    assert mb.geom_type.tolist().count(GEOM_HALF_SPACE) == 1 and mb.npairs == ma.npairs == 2
+    oa, ob = oracle_mod.Oracle(ma, dt, prob, params), oracle_mod.Oracle(mb, dt, prob, params)
+    for o in (oa, ob):
+        o.set_q(np.array(guess))
+        o.eval(4)
+    for f in ("tau", "dtau_dqt", "g", "dq"):
+        a, b = oa.get(f), ob.get(f)
+        assert np.nanmax(np.abs(a - b)) <= 1e-9 * max(1.0, np.nanmax(np.abs(a))), f
+    assert np.abs(oa.get("tau")).max() > 1.0  # the foot does push on the ground
+
+
+@pytest.mark.gpu
+def test_half_space_contact_matches_oracle(oracle_mod):
+    from idto_b200 import capi, problems
+    m, dt, prob, params, guess = problems.hopper(T=12, gradients_method=1, model="hopper_half_space")
+    gs = capi.BatchSolver(capi.Model(m), dt, prob, params, 1)
+    oc = oracle_mod.Oracle(m, dt, prob, params)
+    gs.set_q(np.array(guess))
+    oc.set_q(np.array(guess))
+    gs.eval(1)
+    oc.eval(1)
+    rel = lambda x, y, s=None: np.nanmax(np.abs(x - y)) / (s or max(1.0, np.nanmax(np.abs(y))))
+    assert rel(gs.get("tau")[0], oc.get("tau")) < 1e-11
+    sc = max(1.0, np.nanmax(np.abs(oc.get("dtau_dqp"))))
+    for f in ("dtau_dqm", "dtau_dqt", "dtau_dqp"):
+        assert rel(gs.get(f)[0], oc.get(f), sc) < 2e-6, f
+    it, _, stats = gs.solve(8)
+    k, _, so = oc.solve(8)
+    assert np.array_equal(stats[0, :, 1], so[:, 1]) and rel(stats[0, :, 0], so[:, 0]) < 1e-6
 
 
 @pytest.mark.gpu
