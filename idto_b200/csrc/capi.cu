@@ -684,7 +684,8 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   alloc(&bf.red, size_t(B) * 8);
   alloc(&bf.part, size_t(B) * (T + 1) * 4);
   bf.stash = nullptr;
-  if (m->dm.npath > 0) alloc(&bf.stash, size_t(B) * T * m->dm.nb * 48);
+  bf.stash_half = size_t(B) * T * m->dm.nb * 48;
+  if (m->dm.npath > 0) alloc(&bf.stash, 2 * bf.stash_half);
   alloc(&s->mpc_in, size_t(B) * (1 + nq + nv) + nq);
   ok = ok && A.get(&bf.cnt, B) == cudaSuccess;
   ok = ok && A.get(&bf.ctl, B) == cudaSuccess && A.get(&bf.status, 1) == cudaSuccess;

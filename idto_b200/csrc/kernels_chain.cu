@@ -229,37 +229,43 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
 }
 
 // tau_t = ID(q_{t+1}, v_{t+1}, a_t): one CG-lane group per (b, t).
-// STASH: the same evaluation for the state trajectory, gated on derivs_dirty, that writes the per-body records
-// for the path columns (kernels_path.cu) instead of tau.
+// STASH: additionally write the per-body records of the evaluation for the path columns (kernels_path.cu) into
+// the half of `stash` that belongs to this trajectory: ctl[b].stash_sel for the state, the other one for the
+// scratch trajectory (k_trust_update flips stash_sel when it adopts the scratch trajectory).
 template <int CG, int NLEV, bool STASH = false>
 __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc, TrajBuf tb, double* __restrict__ stash,
+                                                   size_t stash_half, int scratch,
                                                    const ProbCtl* __restrict__ ctl, int force) {
   extern __shared__ __align__(16) unsigned char smem[];
+  const int T = sc.T, nq = sc.nq, nv = sc.nv;
+  const int groups = blockDim.x / CG, grp = threadIdx.x / CG, c = threadIdx.x % CG;
+  const int item = blockIdx.x * groups + grp;
+  const bool in_range = item < sc.B * T;
+  const int b = in_range ? item / T : 0, t = in_range ? item % T : 0;
+  const bool live = in_range && (force || ctl[b].traj_dirty);
+  if (!__syncthreads_or(live ? 1 : 0)) return;  // nothing stale in this CTA (e.g. the evaluation after an accepted step)
   int* si = reinterpret_cast<int*>(smem);
   double* sd = reinterpret_cast<double*>(smem + dm.itab_bytes);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + dm.itab_bytes + dm.dtab_bytes);
   double* base = reinterpret_cast<double*>(smem + model_smem_bytes(dm));
   stage_model(dm, si, sd, bar);
   const CModel C = make_cmodel(dm, si, sd);
-  const int T = sc.T, nq = sc.nq, nv = sc.nv;
-  const int groups = blockDim.x / CG, grp = threadIdx.x / CG, c = threadIdx.x % CG;
   const int gd = cgroup_doubles(dm, nv, 1);
   double* gbase = base + size_t(grp) * gd;
   const EvalSmem S = make_ceval(dm, gbase);
   const PoseSmem PA = make_cpose_private(dm, gbase + ceval_doubles(dm));
   double* T0 = gbase + ceval_doubles(dm) + cpose_private_doubles(dm);
-  const int item = blockIdx.x * groups + grp;
-  const bool in_range = item < sc.B * T;
-  const int b = in_range ? item / T : 0, t = in_range ? item % T : 0;
-  const bool live = in_range && (force || (STASH ? ctl[b].derivs_dirty : ctl[b].traj_dirty));
   Perturb none;
   none.owner = -1, none.local = 0, none.sl = 0, none.quatcol = false;
   none.dq = none.cv = none.ca = 0.0, none.uv = none.ua = 1.0, none.nv3 = none.na3 = {0, 0, 0};
-  // (groups that are not live write their records to the slot of item (0, 0): same values as its owner)
-  double* rec = STASH ? stash + (size_t(live ? b : 0) * T + (live ? t : 0)) * dm.nb * kStashDoubles : nullptr;
+  // (groups that are not live evaluate item (0, 0) and write its records: same values as its owner writes, or,
+  // if problem 0 is not stale, as are there already)
+  double* rec = STASH ? stash + size_t(ctl[live ? b : 0].stash_sel ^ scratch) * stash_half +
+                            (size_t(live ? b : 0) * T + (live ? t : 0)) * dm.nb * kStashDoubles
+                      : nullptr;
   const double* qrow = tb.q + (size_t(live ? b : 0) * (T + 1) + (live ? t : 0) + 1) * nq;
   PairWalk pw;
-  if (dm.prune && !STASH && tb.near && live) {
+  if (dm.prune && tb.near && live) {
     // what a finite-difference perturbation of one coordinate (|dq| <= 2 sqrt(eps) max(1,|q_i|), cc:506, 763) can
     // move a geometry centre by: |dq| times a lever arm bounded by the chain lengths plus the joint travel
     double qmax = 1.0;
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
                                          tb.v + (size_t(live ? b : 0) * (T + 1) + (live ? t : 0) + 1) * nv,
                                          tb.a + (size_t(live ? b : 0) * T + (live ? t : 0)) * nv, none, T0, rec, pw);
   __syncwarp();
-  if (live && !STASH) {
+  if (live) {
     double* tau = tb.tau + (size_t(b) * T + t) * nv;
     for (int r = c; r < nv; r += CG) tau[r] = T0[r];
   }
@@ -281,8 +287,7 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
 template <int CG, int NLEV>
 static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
                                      cudaStream_t stream) {
-  launch_stash_chain(dm, sc, bf, force, stream);  // base records for the path columns (no-op without any)
-  launch_partials_path(dm, sc, bf, force, stream);
+  launch_partials_path(dm, sc, bf, force, stream);  // (the base records come from the trajectory stage)
   if (dm.nfull == 0) return;
   const ChainLayout L = chain_layout(dm, dm.nfull, sc.nv, sc.method == IDTO_GRAD_CENTRAL4 ? 3 : 2);
   const int grid = (sc.B * sc.T + L.slots - 1) / L.slots * L.nsplit;
@@ -307,32 +312,24 @@ static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc,
 }
 
 template <int CG, int NLEV>
-static void launch_tau_chain_cl(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl,
+static void launch_tau_chain_cl(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch,
                                 bool force, cudaStream_t stream) {
   const int threads = 64, groups = threads / CG;  // 2560 (b,t) items x CG lanes: small CTAs reach every SM
   const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv, 1) * 8;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_tau_chain<CG, NLEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    attr_set = true;
-  }
-  g_launch_counter += 1;
-  k_tau_chain<CG, NLEV><<<(sc.B * sc.T + groups - 1) / groups, threads, smem, stream>>>(dm, sc, tb, nullptr, ctl, force);
-}
-
-template <int CG, int NLEV>
-static void launch_stash_chain_cl(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
-                                  cudaStream_t stream) {
-  const int threads = 64, groups = threads / CG;
-  const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv, 1) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
     cudaFuncSetAttribute(k_tau_chain<CG, NLEV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr_set = true;
   }
   g_launch_counter += 1;
-  k_tau_chain<CG, NLEV, true><<<(sc.B * sc.T + groups - 1) / groups, threads, smem, stream>>>(dm, sc, bf.st, bf.stash,
-                                                                                             bf.ctl, force);
+  const TrajBuf& tb = scratch ? bf.sc : bf.st;
+  const int grid = (sc.B * sc.T + groups - 1) / groups;
+  if (bf.stash)
+    k_tau_chain<CG, NLEV, true><<<grid, threads, smem, stream>>>(dm, sc, tb, bf.stash, bf.stash_half, scratch ? 1 : 0,
+                                                                 bf.ctl, force);
+  else
+    k_tau_chain<CG, NLEV><<<grid, threads, smem, stream>>>(dm, sc, tb, nullptr, 0, 0, bf.ctl, force);
 }
 
 // Instantiated (lanes per evaluation, padded tree depth) pairs; anything else falls back to the
@@ -376,14 +373,9 @@ void launch_partials_chain(const DevModel& dm, const SolverConsts& sc, const Sol
                            cudaStream_t stream) {
   IDTO_CHAIN_DISPATCH(launch_partials_chain_cl, dm, sc, bf, force, stream)
 }
-void launch_stash_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
-                        cudaStream_t stream) {
-  if (dm.npath == 0) return;
-  IDTO_CHAIN_DISPATCH(launch_stash_chain_cl, dm, sc, bf, force, stream)
-}
-void launch_tau_chain(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl, bool force,
+void launch_tau_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch, bool force,
                       cudaStream_t stream) {
-  IDTO_CHAIN_DISPATCH(launch_tau_chain_cl, dm, sc, tb, ctl, force, stream)
+  IDTO_CHAIN_DISPATCH(launch_tau_chain_cl, dm, sc, bf, scratch, force, stream)
 }
 
 }  // namespace idto

@@ -13,7 +13,7 @@
 // tau: it restarts the outward pass at the owner from the parent's state, walks down the chain (pose,
 // velocity, acceleration, inertial + gravity force, contact), then walks the inward pass up to the root,
 // adding the unchanged siblings' subtree totals.  Everything unchanged comes from the per-body records of
-// the base evaluations E_t = ID(q_{t+1}, v_{t+1}, a_t) that k_stash_chain wrote to HBM (48 doubles per
+// the base evaluations E_t = ID(q_{t+1}, v_{t+1}, a_t) that k_tau_chain wrote to HBM (48 doubles per
 // body; 12.8 MB for 64 x 40 x 13 bodies, L2 resident): A perturbs E_{t-1}, B perturbs E_t, C (mass-matrix
 // column) needs the pose of E_{t+1}.  The arithmetic per body and the order of every accumulation are
 // those of chain_eval, so the unaffected rows are exactly zero and the affected ones agree with the full
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(128) k_partials_path(DevModel dm, SolverConsts
   const double* qB = bf.st.q + size_t(b) * (T + 1) * nq;
   const double* vB = bf.st.v + size_t(b) * (T + 1) * nv;
   const double* aB = bf.st.a + size_t(b) * T * nv;
-  const double* stB = bf.stash + size_t(b) * T * dm.nb * kStashDoubles;
+  const double* stB = bf.stash + size_t(bf.ctl[b].stash_sel) * bf.stash_half + size_t(b) * T * dm.nb * kStashDoubles;
   auto rec_of = [&](int tt) { return stB + size_t(tt) * dm.nb * kStashDoubles; };
   const double eps = 1.4901161193847656e-08;  // sqrt(2^-52)
   const double qi = qB[size_t(t) * nq + i];

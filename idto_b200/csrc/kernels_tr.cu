@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(kRowThreads) k_trust_update(SolverConsts sc, S
     if (accept) {
       bf.st.cost[b] = bf.sc.cost[b];
       ctl->derivs_dirty = 1;
+      ctl->stash_sel ^= 1;  // the scratch evaluation's per-body records are now those of the state
       if (sc.check_convergence) ctl->pending = 1;
     } else {
       ctl->derivs_dirty = 0;

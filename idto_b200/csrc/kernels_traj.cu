@@ -203,7 +203,7 @@ void launch_tau(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf
                 cudaStream_t stream) {
   const TrajBuf& tb = scratch ? bf.sc : bf.st;
   if (use_chain_kernels(dm)) {
-    launch_tau_chain(dm, sc, tb, bf.ctl, force, stream);
+    launch_tau_chain(dm, sc, bf, scratch, force, stream);
     g_launch_counter += 1;
     k_cost<<<sc.B, 256, 0, stream>>>(sc, tb, bf.q_nom, bf.v_nom, bf.ctl, force ? 1 : 0, scratch ? 0 : 1);
     return;

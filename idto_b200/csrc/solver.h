@@ -89,7 +89,8 @@ struct ProbCtl {
   int iters;         // iterations recorded so far in this idto_solve call
   int reason;        // ConvergenceReason bits
   int pending;       // convergence check of the last accepted step still to be evaluated
-  int pad;
+  int stash_sel;     // which half of SolverBufs::stash holds the records of the STATE trajectory (the other half
+                     // receives those of the scratch trajectory; an accepted step flips it)
 };
 
 struct SolverBufs {
@@ -103,7 +104,8 @@ struct SolverBufs {
   double *X, *S, *rhs;                  // Lagrange multiplier workspace
   double *pH, *dq, *dqH, *tmp1, *tmp2;
   double* red;                          // [B][8] reduction scratch (gHg, gg, ...)
-  double* stash;                        // [B][T][nb][48] per-body records of the base evaluations (kernels_path.cu)
+  double* stash;                        // [2][B][T][nb][48] per-body records of the base evaluations (kernels_path.cu)
+  size_t stash_half;                    // doubles between the two halves (full batch, also in sub-batch views)
   double* part;                         // [B][T+1][4] per-block-row partial sums of the row-parallel mat-vecs
   int* cnt;                             // [B] arrival counters of the "last CTA of the problem" election
   ProbCtl* ctl;
@@ -142,12 +144,12 @@ bool chain_supported(const DevModel& dm);
 int chain_min_smem_bytes(const DevModel& dm, int nv, int method);  // one-slot CTA of the chain-lane ID kernels
 void launch_partials_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
                            cudaStream_t stream);
-// single-lane subtree evaluations for the path columns (after launch_stash_chain filled bf.stash)
+// single-lane subtree evaluations for the path columns (records of the base evaluations: bf.stash)
 void launch_partials_path(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
                           cudaStream_t stream);
-void launch_stash_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
-                        cudaStream_t stream);
-void launch_tau_chain(const DevModel& dm, const SolverConsts& sc, const TrajBuf& tb, const ProbCtl* ctl, bool force,
+// tau of the state (scratch = false) or scratch trajectory; with path columns it also writes the per-body records
+// of the evaluation into the state's (scratch's) half of bf.stash
+void launch_tau_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch, bool force,
                       cudaStream_t stream);
 bool use_chain_kernels(const DevModel& dm);  // chain-lane kernels unless IDTO_DYNAMICS=group or unsupported
 extern long g_launch_counter;  // kernels launched by this library (all solvers)
