@@ -1050,8 +1050,12 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
     if (int rc = solve_enqueue(s, max_iterations)) return rc;
     for (const Part& p : make_parts(s)) {
       const size_t o = size_t(p.b0), nb = size_t(p.sc.B);
-      launch_traj(s->model->dm, p.sc, p.bf, false, false, p.st);  // solution = {q, EvalV, EvalTau}
-      launch_tau(s->model->dm, p.sc, p.bf, false, false, p.st);
+      // solution = {q, EvalV, EvalTau} (cc:2636-2638): current after any iteration (its first stage evaluates a
+      // stale trajectory, an accepted step adopts the scratch one), so only a 0-iteration call evaluates here
+      if (max_iterations == 0) {
+        launch_traj(s->model->dm, p.sc, p.bf, false, false, p.st);
+        launch_tau(s->model->dm, p.sc, p.bf, false, false, p.st);
+      }
       if (q_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(q_out + o * T1 * c.nq, p.bf.st.q, nb * T1 * c.nq * 8, cudaMemcpyDeviceToHost, p.st));
       if (v_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(v_out + o * T1 * c.nv, p.bf.st.v, nb * T1 * c.nv * 8, cudaMemcpyDeviceToHost, p.st));
       if (tau_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(tau_out + o * c.T * c.nv, p.bf.st.tau, nb * c.T * c.nv * 8, cudaMemcpyDeviceToHost, p.st));
@@ -1073,8 +1077,8 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
   if (q_guess || q_init || v_init || q_nom || v_nom)
     k_set_ctl<<<(c.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, c.B, 1, 0.0);
   if (int rc = solve_enqueue(s, max_iterations)) return rc;
-  // solution = {q, EvalV, EvalTau} (cc:2636-2638)
-  enqueue_trajectory(s, false, false);
+  // solution = {q, EvalV, EvalTau} (cc:2636-2638); see the sub-stream branch
+  if (max_iterations == 0) enqueue_trajectory(s, false, false);
   if (q_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(q_out, s->bf.st.q, B * T1 * c.nq * 8, cudaMemcpyDeviceToHost, s->stream));
   if (v_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(v_out, s->bf.st.v, B * T1 * c.nv * 8, cudaMemcpyDeviceToHost, s->stream));
   if (tau_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(tau_out, s->bf.st.tau, B * c.T * c.nv * 8, cudaMemcpyDeviceToHost, s->stream));
