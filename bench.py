@@ -279,7 +279,7 @@ def main():
                     "peak_tflops": 148 * 64 * 2 * 1.965e9 / 1e12, "source": "ncu instruction counts, profiles/ncu_traffic.json"}
     except OSError:
         pass
-    roofline = {"kernel": "id_partials stage: k_tau_chain<stash> + k_partials_path + k_partials_chain", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "id_partials stage: k_partials_path + k_partials_chain", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
                 "avg_launch_ms": stage_ms["id_partials"],
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
