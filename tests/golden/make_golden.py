@@ -66,7 +66,8 @@ def oracle_case(name, T, seed, amp):
 if __name__ == "__main__":
     with open(os.path.join(HERE, "reference_anchors.json"), "w") as f:
         json.dump(reference_anchors(), f, indent=1)
-    for name, T, seed, amp in (("hopper", 10, 21, 0.05), ("mini_cheetah", 6, 22, 0.03), ("spinner", 8, 23, 0.05)):
+    for name, T, seed, amp in (("hopper", 10, 21, 0.05), ("mini_cheetah", 6, 22, 0.03), ("spinner", 8, 23, 0.05),
+                               ("allegro_hand", 4, 24, 0.01)):
         np.savez_compressed(os.path.join(HERE, f"oracle_{name}.npz"), **oracle_case(name, T, seed, amp))
     print(open(os.path.join(HERE, "reference_anchors.json")).read()[:600])
     print({f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE))})
