@@ -143,7 +143,7 @@ def main():
     config = {"workload": f"mini_cheetah trot (floating base + 12 DOF, 4 foot-ground pairs), T={T}, "
                           f"batch={args.batch} independent MPC re-solves per GPU, 1 iteration per step, "
                           f"gradients={args.method}_differences, equality_constraints=on, scaling=double_sqrt",
-              "model": "mini_cheetah_with_ground", "nq": m.nq, "nv": m.nv, "T": T, "batch_per_gpu": args.batch,
+              "urdf": "mini_cheetah_with_ground", "nq": m.nq, "nv": m.nv, "T": T, "batch_per_gpu": args.batch,
               "l2": "flushed before every step (160 MiB memset in stream order, inside the timed region; L2 = 126 MB)"}
 
     if args.impl == "reference":
