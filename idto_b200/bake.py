@@ -696,6 +696,9 @@ def bake_reference_models(reference_root="/root/reference", out_dir=_MODEL_DIR):
     b.add_rigid_body("ball", 0.05, [0.0, 0.0, 0.0], 0.4 * 0.05 * 0.06 ** 2 * np.eye(3))
     b.register_collision_geometry("ball", X(), "sphere", [0.06], "ball_collision")
     out["allegro_hand"] = b.finalize()
+    # --upside_down (allegro_hand.cc:94-97): the same plant with the gravity vector reversed
+    b.gravity = np.array([0.0, 0.0, 9.81])
+    out["allegro_hand_upside_down"] = b.finalize()
     for k, m in out.items():
         m.name = k
         m.save(os.path.join(out_dir, k + ".json"))

@@ -137,6 +137,25 @@ def allegro_hand(T=60, gradients_method=GRAD_FORWARD, max_iterations=1):
     return m, 0.05, prob, params, guess
 
 
+def allegro_hand_upside_down(T=40, gradients_method=GRAD_FORWARD, max_iterations=1):
+    """examples/allegro_hand/allegro_hand_upside_down.yaml:1-106 (`allegro_hand --upside_down`, allegro_hand.cc:94-97:
+    gravity reversed, the ball hangs in the finger tips and is to be turned a quarter turn)."""
+    m = load_model("allegro_hand_upside_down")
+    q0 = [-0.2, 1.4, 0.6, 0.7, 0.3, 1.5, 1.0, 1.0, 0.0, 0.7, 1.0, 1.0, 0.1, 1.0, 1.0, 1.0,
+          1.0, 0.0, 0.0, 0.0, -0.06, 0.0, 0.07]
+    qe = list(q0)
+    qe[16:20] = [0.7, 0.0, 0.0, -0.7]
+    prob = _make(m, T, 0.05, q0, [0.0] * 22, q0, qe,
+                 [1e-2] * 16 + [1e1] * 7, [1e-3] * 16 + [1e0] * 6, [1e-1] * 16 + [1e3] * 6,
+                 [1e-2] * 16 + [1e1] * 7, [1e-3] * 16 + [1e0] * 6)
+    params = SolverParameters(max_iterations=max_iterations, scaling=True, equality_constraints=True,
+                              contact_stiffness=100, dissipation_velocity=0.01, smoothing_factor=0.001,
+                              friction_coefficient=1.0, stiction_velocity=0.03,
+                              gradients_method=gradients_method, verbose=False)
+    guess = [np.array(q0) for _ in range(T + 1)]
+    return m, 0.05, prob, params, guess
+
+
 def pendulum(T=20, dt=0.05, gradients_method=GRAD_FORWARD):
     """optimizer/test/trajectory_optimizer_test.cc:434-490 (PendulumSwingup)."""
     m = load_model("pendulum")

@@ -54,6 +54,24 @@ def test_allegro_oracle_physics(oracle_mod):
     assert k == 3 and np.all(np.isfinite(st[:, 0])) and st[-1, 0] < st[0, 0]
 
 
+def test_allegro_upside_down_variant(oracle_mod):
+    """`allegro_hand --upside_down` (allegro_hand.cc:94-97): the same plant with gravity reversed."""
+    up, dn = load_model("allegro_hand_upside_down"), load_model("allegro_hand")
+    assert up.gravity.tolist() == [0.0, 0.0, 9.81] and dn.gravity.tolist() == [0.0, 0.0, -9.81]
+    assert up.npairs == dn.npairs and np.array_equal(up.X_PF, dn.X_PF) and np.array_equal(up.mass, dn.mass)
+    m, dt, prob, params, guess = problems.allegro_hand_upside_down(T=8, max_iterations=3)
+    oc = oracle_mod.Oracle(m, dt, prob, params)
+    q_far = np.array(guess[0])
+    q_far[20:] = [0.5, 0.5, 0.5]
+    tau, act = oc.inverse_dynamics(q_far, np.zeros(22), np.zeros(22))
+    ball_pairs = m.pair_geomB == m.ngeoms - 1
+    assert not act[ball_pairs].any()  # (some finger-finger and finger-palm pairs do touch in this grasp pose)
+    assert abs(tau[21] + 0.05 * 9.81) < 1e-12 and np.abs(tau[16:21]).max() < 1e-12  # the ball "falls" upwards
+    oc.set_q(np.array(guess))
+    k, _, st = oc.solve(3)
+    assert k == 3 and np.all(np.isfinite(st[:, 0])) and st[-1, 0] < st[0, 0]
+
+
 def _relerr(a, b, scale=None):
     a, b = np.asarray(a, float), np.asarray(b, float)
     scale = max(1.0, float(np.nanmax(np.abs(b)))) if scale is None else scale

@@ -80,7 +80,9 @@ def test_unknown_key_is_an_error_and_off_path_options_are_recorded():
 @pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is not mounted on this box")
 @pytest.mark.parametrize("name,yaml_rel,T", [("acrobot", "acrobot/acrobot.yaml", None),
                                              ("hopper", "hopper/hopper.yaml", None),
-                                             ("allegro_hand", "allegro_hand/allegro_hand.yaml", None)])
+                                             ("allegro_hand", "allegro_hand/allegro_hand.yaml", None),
+                                             ("allegro_hand_upside_down",
+                                              "allegro_hand/allegro_hand_upside_down.yaml", None)])
 def test_reference_example_yaml_equals_restated_problem(name, yaml_rel, T):
     o = yaml_config.load_yaml(os.path.join(REF, yaml_rel))
     m, dt, prob_r, params_r, guess_r = getattr(problems, name)(T=o.num_steps)
