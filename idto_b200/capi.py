@@ -75,6 +75,7 @@ def lib():
         L.idto_mpc_advance.argtypes = [H, _D, _D, _D, _D]
         L.idto_fence.argtypes = [H]
         L.idto_flush_l2.argtypes = [H, ctypes.c_void_p, ctypes.c_size_t]
+        L.idto_debug_pair_trace.argtypes = [H, ctypes.c_int]
         L.idto_launch_count.argtypes = [H]
         L.idto_launch_count.restype = ctypes.c_long
         L.idto_profile_enable.argtypes = [H, ctypes.c_int]
@@ -168,10 +169,16 @@ class BatchSolver:
         _check(lib().idto_invalidate(self.h))
 
     def resolve_async(self, max_iterations, q_guess=None, q_init=None, v_init=None, q_nom=None, v_nom=None,
-                      q_out=None, v_out=None, tau_out=None, stats_out=None):
+                      q_out=None, v_out=None, tau_out=None, stats_out=None, iters_out=None):
         """End-to-end MPC re-solve: arguments are raw host pointers (ints) of pinned buffers or None."""
+        it = None if iters_out is None else ctypes.cast(ctypes.c_void_p(iters_out), _I)
         _check(lib().idto_resolve_async(self.h, int(max_iterations), q_guess, q_init, v_init, q_nom, v_nom, q_out,
-                                        v_out, tau_out, None, stats_out))
+                                        v_out, tau_out, it, stats_out))
+
+    def debug_pair_trace(self, on=True):
+        """Record which contact pairs every inverse-dynamics evaluation applies a force for; then
+        get("pair_active") -> [B, T*npairs], get("pair_active_fd") -> [B, T*nq*4*npairs]."""
+        _check(lib().idto_debug_pair_trace(self.h, int(on)))
 
     def mpc_advance(self, elapsed, q0, v0, q_nom_selector=None):
         """Device-side MPC shell between two re-solves (examples/mpc_controller.cc:43-98): spline-shifted

@@ -72,6 +72,8 @@ struct idto_solver_s {
   // mutable per-batch problem data
   double *q_init, *v_init, *q_nom, *v_nom;
   double* mpc_in = nullptr;  // staging of idto_mpc_advance inputs: [B] elapsed | [B][nq] q0 | [B][nv] v0 | [nq] selector
+  int* iters_dev = nullptr;    // [B] ProbCtl::iters packed for the asynchronous D2H of idto_resolve_async
+  double* delta_in = nullptr;  // [B] staging of idto_set_delta (bf.red holds the cached dogleg scalars: not scratch)
   long launches0 = 0;
   bool profile = false;
   std::map<std::string, std::vector<ProfEvent>> prof;
@@ -126,11 +128,20 @@ struct Prof {
 // Stage pipeline; each stage is gated on the per-problem dirty flags unless force is set.
 void enqueue_trajectory(idto_solver_s* s, bool scratch, bool force) {
   Prof p(s, scratch ? "trajectory_scratch" : "trajectory");
+  if (s->bf.act_base && !scratch)  // debug trace: evaluate every problem so that the whole trace is rewritten
+    cudaMemsetAsync(s->bf.act_base, 0, size_t(s->sc.B) * s->sc.T * std::max(s->model->dm.np, 1) * sizeof(int), s->stream),
+        force = true;
   launch_traj(s->model->dm, s->sc, s->bf, scratch, force, s->stream);
   launch_tau(s->model->dm, s->sc, s->bf, scratch, force, s->stream);
 }
 void enqueue_derivatives(idto_solver_s* s, bool force) {
   Prof p(s, "id_partials");
+  if (s->bf.act_fd) {  // debug trace: 0xff.. = -1 = "pair not visited by this evaluation"; pruned models report the
+    // pairs of their compacted list only, so their trace starts from 0
+    cudaMemsetAsync(s->bf.act_fd, s->model->dm.prune ? 0 : 0xff,
+                    size_t(s->sc.B) * s->sc.T * s->sc.nq * 4 * std::max(s->model->dm.np, 1) * sizeof(int), s->stream);
+    force = true;
+  }
   launch_partials(s->model->dm, s->sc, s->bf, force, s->stream);
 }
 void enqueue_assembly(idto_solver_s* s, bool force) {
@@ -201,7 +212,7 @@ struct Part {
   cudaStream_t st;
   int b0;
 };
-bool multi(const idto_solver_s* s) { return s->nsub > 1 && !s->profile; }
+bool multi(const idto_solver_s* s) { return s->nsub > 1 && !s->profile && !s->bf.act_base; }
 std::vector<Part> make_parts(const idto_solver_s* s) {
   std::vector<Part> parts(s->nsub);
   for (int i = 0; i < s->nsub; ++i) {
@@ -278,6 +289,10 @@ __global__ void k_set_delta(ProbCtl* ctl, const double* d, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) ctl[b].Delta = d[b];
 }
+__global__ void k_pack_iters(const ProbCtl* ctl, int* out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = ctl[b].iters;
+}
 __global__ void k_fill(double* p, size_t n, double v) {
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = v;
 }
@@ -324,6 +339,8 @@ int check_status(idto_solver_s* s) {
     if (st == IDTO_ERR_CONTACT_OVERFLOW)
       set_last_error("more than " + std::to_string(kMaxActivePairs) +
                      " contact pairs within the activation distance in one inverse-dynamics evaluation");
+    else if (st == IDTO_ERR_UNSUPPORTED)
+      set_last_error("no KKT sweep kernel for this block size");
     else
       set_last_error("penta-diagonal factorisation failed (singular diagonal block)");
     int zero = 0;
@@ -617,6 +634,16 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
     return IDTO_ERR_UNSUPPORTED;
   }
   {
+    // the KKT sweeps and the row-parallel mat-vecs keep one block row per warp (lane = row): block size <= 32
+    const int nu = int(m->unactuated.size());
+    const int kb = nq + ((p->equality_constraints && nu > 0) ? nu : 0);
+    if (nq > 32 || kb > 32) {
+      set_last_error("KKT block size nq + num_unactuated = " + std::to_string(kb) + " (nq = " + std::to_string(nq) +
+                     "): the penta-diagonal kernels support block sizes up to 32");
+      return IDTO_ERR_UNSUPPORTED;
+    }
+  }
+  {
     const bool chain = use_chain_kernels(m->dm);
     if (m->dm.prune && !chain) {
       set_last_error("models with more than " + std::to_string(kMaxActivePairs) +
@@ -633,7 +660,8 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   }
   auto* s = new idto_solver_s();
   s->model = m, s->params = *p;
-  cudaGetDevice(&s->device);
+  cudaSetDevice(m->device);  // the workspace lives on the device that holds the baked tables
+  s->device = m->device;
   SolverConsts& sc = s->sc;
   sc.B = B, sc.T = T, sc.nq = nq, sc.nv = nv, sc.nu = int(m->unactuated.size());
   sc.n = (T + 1) * nq, sc.nh = sc.nu * T, sc.dt = pd->time_step;
@@ -687,6 +715,8 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   bf.stash_half = size_t(B) * T * m->dm.nb * 48;
   if (m->dm.npath > 0) alloc(&bf.stash, 2 * bf.stash_half);
   alloc(&s->mpc_in, size_t(B) * (1 + nq + nv) + nq);
+  alloc(&s->delta_in, B);
+  ok = ok && A.get(&s->iters_dev, B) == cudaSuccess;
   ok = ok && A.get(&bf.cnt, B) == cudaSuccess;
   ok = ok && A.get(&bf.ctl, B) == cudaSuccess && A.get(&bf.status, 1) == cudaSuccess;
   if (!ok) {
@@ -697,6 +727,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   }
   bf.q_init = s->q_init, bf.v_init = s->v_init, bf.q_nom = s->q_nom, bf.v_nom = s->v_nom;
   bf.stats = nullptr, bf.stats_cap = 0;
+  bf.act_base = bf.act_fd = nullptr;
   sc.Qq = dQq, sc.Qv = dQv, sc.Qfq = dQfq, sc.Qfv = dQfv, sc.R = dR, sc.unact = dun, sc.quat_starts = dqs;
   sc.status = bf.status;
   auto up_diag = [&](double* dst, const double* Mx, int n) {
@@ -742,6 +773,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
 
 int idto_solver_destroy(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
   cudaDeviceSynchronize();
   for (auto st : s->sub_streams) cudaStreamDestroy(st);
@@ -757,6 +789,7 @@ int idto_solver_destroy(idto_solver_t s) {
 
 int idto_solver_set_substreams(idto_solver_t s, int n) {
   if (!s || n < 1 || n > 16) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   if (n > s->sc.B) n = s->sc.B;
   use_main(s);
   cudaStreamSynchronize(s->stream);
@@ -777,12 +810,14 @@ int idto_solver_set_substreams(idto_solver_t s, int n) {
 
 int idto_solver_set_stream(idto_solver_t s, void* stream) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   s->stream = static_cast<cudaStream_t>(stream);
   return IDTO_OK;
 }
 
 int idto_set_q(idto_solver_t s, const double* q) {
   if (!s || !q) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->bf.st.q, q, size_t(s->sc.B) * s->sc.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 1, 0.0);
@@ -790,6 +825,7 @@ int idto_set_q(idto_solver_t s, const double* q) {
 }
 int idto_invalidate(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   if (multi(s)) {
     use_subs(s);
     for (const Part& p : make_parts(s)) k_set_ctl<<<(p.sc.B + 127) / 128, 128, 0, p.st>>>(p.bf.ctl, p.sc.B, 1, 0.0);
@@ -801,6 +837,7 @@ int idto_invalidate(idto_solver_t s) {
 }
 int idto_reset_initial_conditions(idto_solver_t s, const double* q0, const double* v0) {
   if (!s || !q0 || !v0) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->q_init, q0, size_t(s->sc.B) * s->sc.nq * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->v_init, v0, size_t(s->sc.B) * s->sc.nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
@@ -809,6 +846,7 @@ int idto_reset_initial_conditions(idto_solver_t s, const double* q0, const doubl
 }
 int idto_update_nominal_trajectory(idto_solver_t s, const double* qn, const double* vn) {
   if (!s || !qn || !vn) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
   const size_t T1 = s->sc.T + 1;
   IDTO_CUDA_CHECK(cudaMemcpyAsync(s->q_nom, qn, size_t(s->sc.B) * T1 * s->sc.nq * sizeof(double), cudaMemcpyHostToDevice, s->stream));
@@ -818,21 +856,24 @@ int idto_update_nominal_trajectory(idto_solver_t s, const double* qn, const doub
 }
 int idto_set_delta(idto_solver_t s, const double* delta) {
   if (!s || !delta) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
-  IDTO_CUDA_CHECK(cudaMemcpyAsync(s->bf.red, delta, s->sc.B * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  k_set_delta<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->bf.red, s->sc.B);
+  IDTO_CUDA_CHECK(cudaMemcpyAsync(s->delta_in, delta, s->sc.B * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  k_set_delta<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->delta_in, s->sc.B);
   return IDTO_OK;
 }
 int idto_get_delta(idto_solver_t s, double* delta) { return idto_get(s, "delta", delta); }
 
 int idto_eval_trajectory(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
   enqueue_trajectory(s, false, false);
   return check_status(s);
 }
 int idto_eval_derivatives(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
   enqueue_trajectory(s, false, false);
   enqueue_derivatives(s, false);
@@ -840,6 +881,7 @@ int idto_eval_derivatives(idto_solver_t s) {
 }
 int idto_eval_assembly(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
   enqueue_trajectory(s, false, false);
   enqueue_derivatives(s, false);
@@ -849,6 +891,7 @@ int idto_eval_assembly(idto_solver_t s) {
 }
 int idto_eval_dogleg(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   if (int rc = idto_eval_assembly(s)) return rc;
   k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 2, 0.0);
   launch_dogleg(s->sc, s->bf, s->stream);
@@ -856,6 +899,7 @@ int idto_eval_dogleg(idto_solver_t s) {
 }
 int idto_eval_trust_ratio(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   if (int rc = idto_eval_dogleg(s)) return rc;
   enqueue_trajectory(s, true, true);
   launch_trust_update(s->model->dm, s->sc, s->bf, false, s->stream);
@@ -864,6 +908,7 @@ int idto_eval_trust_ratio(idto_solver_t s) {
 
 long idto_field_size(idto_solver_t s, const char* field) {
   if (!s || !field) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   const SolverConsts& c = s->sc;
   const std::string f(field);
   const long T = c.T, nq = c.nq, nv = c.nv;
@@ -877,6 +922,9 @@ long idto_field_size(idto_solver_t s, const char* field) {
   if (f == "g" || f == "D" || f == "gs" || f == "gm" || f == "dq" || f == "dqH") return c.n;
   if (f == "H_A" || f == "H_B" || f == "H_C" || f == "Hs_A" || f == "Hs_B" || f == "Hs_C") return (T + 1) * nq * nq;
   if (f == "J") return long(c.nh) * c.n;
+  if (f == "dvt_dqt" || f == "dvt_dqm") return (T + 1) * nv * nq;
+  if (f == "pair_active") return s->bf.act_base ? T * long(s->model->dm.np) : IDTO_ERR_INVALID_ARG;
+  if (f == "pair_active_fd") return s->bf.act_fd ? T * nq * 4 * long(s->model->dm.np) : IDTO_ERR_INVALID_ARG;
   {  // debugging views of the KKT sweep (block size kb = nq + nu when equality constraints are on)
     const long kb = nq + (c.eq ? c.nu : 0);
     if (f == "dbg_FY" || f == "dbg_FZ") return (T + 1) * kb * kb;
@@ -887,6 +935,7 @@ long idto_field_size(idto_solver_t s, const char* field) {
 
 int idto_get(idto_solver_t s, const char* field, double* out) {
   if (!s || !field || !out) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   const long sz = idto_field_size(s, field);
   if (sz < 0) return IDTO_ERR_INVALID_ARG;
   const SolverConsts& c = s->sc;
@@ -926,6 +975,25 @@ int idto_get(idto_solver_t s, const char* field, double* out) {
   else if (f == "dbg_Fr") src = bf.X;
   if (src) {
     IDTO_CUDA_CHECK(cudaMemcpy(out, src, size_t(sz) * c.B * sizeof(double), cudaMemcpyDeviceToHost));
+    return IDTO_OK;
+  }
+  if (f == "dvt_dqt" || f == "dvt_dqm") {  // VelocityPartials (velocity_partials.h:19-39, cc:962-973): +-N+_t / dt
+    IDTO_CUDA_CHECK(cudaMemcpy(out, bf.st.Nplus, size_t(sz) * c.B * sizeof(double), cudaMemcpyDeviceToHost));
+    const bool qm = f == "dvt_dqm";
+    const size_t blk = size_t(c.nv) * c.nq;
+    for (int b = 0; b < c.B; ++b)
+      for (int t = 0; t <= c.T; ++t) {
+        double* N = out + (size_t(b) * (c.T + 1) + t) * blk;
+        for (size_t e = 0; e < blk; ++e)
+          N[e] = qm ? (t == 0 ? std::numeric_limits<double>::quiet_NaN() : -N[e] / c.dt) : N[e] / c.dt;
+      }
+    return IDTO_OK;
+  }
+  if (f == "pair_active" || f == "pair_active_fd") {
+    std::vector<int> tmp(size_t(sz) * c.B);
+    IDTO_CUDA_CHECK(cudaMemcpy(tmp.data(), f == "pair_active" ? bf.act_base : bf.act_fd, tmp.size() * sizeof(int),
+                               cudaMemcpyDeviceToHost));
+    for (size_t e = 0; e < tmp.size(); ++e) out[e] = double(tmp[e]);
     return IDTO_OK;
   }
   if (f == "J") {  // expand the three bands into the reference's dense (nu*T) x n, column-major
@@ -1021,6 +1089,7 @@ static int solve_collect(idto_solver_t s, int max_iterations, int* iters_out, in
 
 int idto_solve(idto_solver_t s, int max_iterations, int* iters_out, int* reason_out, double* stats_out) {
   if (!s || max_iterations < 0) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   if (int rc = solve_enqueue(s, max_iterations)) return rc;
   if (int rc = check_status(s)) return rc;
   return solve_collect(s, max_iterations, iters_out, reason_out, stats_out);
@@ -1030,6 +1099,7 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
                        const double* v_init, const double* q_nom, const double* v_nom, double* q_out, double* v_out,
                        double* tau_out, int* iters_out, double* stats_out) {
   if (!s || max_iterations < 0) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   const SolverConsts& c = s->sc;
   const size_t T1 = c.T + 1, B = c.B;
   if (multi(s)) {
@@ -1064,8 +1134,11 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
                                           size_t(max_iterations) * IDTO_NUM_STATS * 8, p.bf.stats,
                                           s->bf.stats_cap * IDTO_NUM_STATS * 8,
                                           size_t(max_iterations) * IDTO_NUM_STATS * 8, nb, cudaMemcpyDeviceToHost, p.st));
+      if (iters_out) {  // rows of stats_out beyond iters_out[b] are not written by this call (early convergence)
+        k_pack_iters<<<(p.sc.B + 127) / 128, 128, 0, p.st>>>(p.bf.ctl, s->iters_dev + o, p.sc.B);
+        IDTO_CUDA_CHECK(cudaMemcpyAsync(iters_out + o, s->iters_dev + o, nb * sizeof(int), cudaMemcpyDeviceToHost, p.st));
+      }
     }
-    (void)iters_out;
     return IDTO_OK;
   }
   use_main(s);
@@ -1093,13 +1166,17 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
                                         s->stream));
     }
   }
-  (void)iters_out;
+  if (iters_out) {
+    k_pack_iters<<<(c.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->iters_dev, c.B);
+    IDTO_CUDA_CHECK(cudaMemcpyAsync(iters_out, s->iters_dev, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  }
   return IDTO_OK;
 }
 
 int idto_mpc_advance(idto_solver_t s, const double* elapsed, const double* q0, const double* v0,
                      const double* q_nom_selector) {
   if (!s || !elapsed || !q0 || !v0) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   const SolverConsts& c = s->sc;
   const size_t B = c.B;
   use_main(s);
@@ -1122,12 +1199,14 @@ int idto_mpc_advance(idto_solver_t s, const double* elapsed, const double* q0, c
 
 int idto_fence(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);  // joins the sub-streams into the caller's stream; later sub-stream work forks after it
   return IDTO_OK;
 }
 
 int idto_flush_l2(idto_solver_t s, void* scratch, size_t bytes) {
   if (!s || !scratch) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   if (multi(s)) {
     use_subs(s);
     const size_t share = bytes / s->nsub;
@@ -1142,14 +1221,39 @@ int idto_flush_l2(idto_solver_t s, void* scratch, size_t bytes) {
 
 int idto_synchronize(idto_solver_t s) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
   return check_status(s);
+}
+
+int idto_debug_pair_trace(idto_solver_t s, int enable) {
+  if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);
+  use_main(s);
+  IDTO_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+  if (!enable) {  // (the buffers stay allocated until the solver is destroyed)
+    s->bf.act_base = s->bf.act_fd = nullptr;
+    return IDTO_OK;
+  }
+  if (!use_chain_kernels(s->model->dm)) {
+    set_last_error("the contact-pair trace is implemented by the chain-lane inverse-dynamics kernels only");
+    return IDTO_ERR_UNSUPPORTED;
+  }
+  const size_t np = size_t(std::max(s->model->dm.np, 1)), BT = size_t(s->sc.B) * s->sc.T;
+  if (s->mem.get(&s->bf.act_base, BT * np) != cudaSuccess || s->mem.get(&s->bf.act_fd, BT * s->sc.nq * 4 * np) != cudaSuccess) {
+    s->bf.act_base = s->bf.act_fd = nullptr;
+    set_last_error("cudaMalloc failed for the contact-pair trace");
+    return IDTO_ERR_CUDA;
+  }
+  k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 1, 0.0);  // re-evaluate everything
+  return IDTO_OK;
 }
 
 long idto_launch_count(idto_solver_t s) { return s ? g_launch_counter - s->launches0 : IDTO_ERR_INVALID_ARG; }
 
 int idto_profile_enable(idto_solver_t s, int enable) {
   if (!s) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
   cudaStreamSynchronize(s->stream);
   for (auto& kv : s->prof)
@@ -1161,6 +1265,7 @@ int idto_profile_enable(idto_solver_t s, int enable) {
 
 int idto_profile_read(idto_solver_t s, const char* kernel, double* total_ms, long* launches) {
   if (!s || !kernel) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   IDTO_CUDA_CHECK(cudaStreamSynchronize(s->stream));
   double tot = 0.0;
   long n = 0;

@@ -21,6 +21,17 @@ void set_last_error(const std::string& msg);
     }                                                                                           \
   } while (0)
 
+// Function attributes (dynamic shared-memory limits) are per device: every launcher keeps one flag per device.
+constexpr int kMaxDevices = 64;
+inline bool first_use_on_device(bool (&flags)[kMaxDevices]) {
+  int d = 0;
+  cudaGetDevice(&d);
+  if (d < 0 || d >= kMaxDevices) return true;
+  if (flags[d]) return false;
+  flags[d] = true;
+  return true;
+}
+
 // ------------------------------------------------------------------ 3-vector algebra
 struct V3 {
   double x, y, z;

@@ -149,6 +149,8 @@ struct PairWalk {
   int* near_out = nullptr;       // pruned models: write the near list of this (unperturbed) pose
   double margin = 0.0;           // near_out: distance <= threshold + margin
   bool skip = false;             // no contact geometry wanted (pose used by bias-free evaluations only)
+  int* act_out = nullptr;        // debug trace (idto_debug_pair_trace): [np] flags, 1 for every candidate pair whose
+                                 // force this evaluation computes (the caller zero-fills it); may differ per group
 };
 
 // One inverse-dynamics evaluation by a group of CG lanes (all 32 lanes of the warp must call).
@@ -387,12 +389,18 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
           if (count > pst || (pw.near_out && ncount > kMaxActivePairs)) atomicExch(sc.status, IDTO_ERR_CONTACT_OVERFLOW);
         }
         __syncwarp();
+        if (pw.act_out) {  // what the force pass will walk: the compacted list, read back from shared memory
+          const int cnt = min(int(ids[pst]), pst);
+          for (int is = c; is < cnt; is += CG) pw.act_out[slot_pair(ids, is, M.np)] = 1;
+        }
       } else if (!pw.skip) {
         for (int ip = c; ip < M.np; ip += CG) {
           const PairGeom pg = pair_geometry(C, Po, ip);
           store_V(Po.PG, pst, ip, pg.nhat);
           store_V(Po.PG + 3 * pst, pst, ip, pg.p_WC);
-          Po.PG[6 * pst + ip] = contact_fn_c(sc, pg.distance);
+          const double fn_c = contact_fn_c(sc, pg.distance);
+          Po.PG[6 * pst + ip] = fn_c;
+          if (pw.act_out) pw.act_out[ip] = fn_c > 0.0 ? 1 : 0;  // the force pass skips slots with fn_c == 0
         }
       }
     }

@@ -343,10 +343,9 @@ void launch_assemble(const DevModel& dm, const SolverConsts& sc, const SolverBuf
   const int alias = ntask <= kAsmThreads ? 1 : 0;
   const int nstage = kNumBlk * blkp, nprod = 8 * npad * npad;
   const int smem = ((alias ? std::max(nstage, nprod) : nstage + nprod) + 6 * sc.nq) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   g_launch_counter += 2;
   k_assemble<<<sc.B*(sc.T + 1), kAsmThreads, smem, stream>>>(sc, bf, force ? 1 : 0, alias);

@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
 #pragma unroll 1
   for (int kk = 0; kk < NK; ++kk) {
     const double m = ((kk & 1) ? -1.0 : 1.0) * ((kk >= 2) ? 2.0 : 1.0);
+    if (bf.act_fd && live) pwA.act_out = bf.act_fd + ((((size_t(b) * T + (t - 1)) * nq + i) * 4 + kk) * dm.np);
     pt.dq = m * dq, pt.cv = m * dv, pt.ca = m * da, pt.uv = 1.0, pt.ua = 1.0, pt.nv3 = nt3, pt.na3 = nt3;
     chain_eval<CG, NLEV, kEvalFull>(C, sc, PA, S, c, qB + size_t(t) * nq, vB + size_t(t) * nv,
                                     aB + size_t(t - 1) * nv, pt, (kk & 1) ? T1 : T0, nullptr, pwA);
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
 template <int CG, int NLEV, bool STASH = false>
 __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc, TrajBuf tb, double* __restrict__ stash,
                                                    size_t stash_half, int scratch,
-                                                   const ProbCtl* __restrict__ ctl, int force) {
+                                                   const ProbCtl* __restrict__ ctl, int force, int* act_base) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int T = sc.T, nq = sc.nq, nv = sc.nv;
   const int groups = blockDim.x / CG, grp = threadIdx.x / CG, c = threadIdx.x % CG;
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
     pw.near_out = tb.near + (size_t(b) * T + t) * kNearStride;
     pw.margin = 4e-7 * qmax * (dm.reach + dm.nb * qmax);
   }
+  if (act_base && live) pw.act_out = act_base + (size_t(b) * T + t) * dm.np;
   chain_eval<CG, NLEV, kEvalFull, STASH>(C, sc, PA, S, c, qrow,
                                          tb.v + (size_t(live ? b : 0) * (T + 1) + (live ? t : 0) + 1) * nv,
                                          tb.a + (size_t(live ? b : 0) * T + (live ? t : 0)) * nv, none, T0, rec, pw);
@@ -294,11 +296,10 @@ static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc,
   g_launch_counter += 1;
 #define IDTO_LAUNCH_PC(METHOD)                                                                                   \
   {                                                                                                              \
-    static bool attr_set = false;                                                                                \
-    if (!attr_set) {                                                                                             \
+    static bool attr_set[kMaxDevices] = {};                                                                                \
+    if (first_use_on_device(attr_set)) {                                                                                             \
       cudaFuncSetAttribute(k_partials_chain<CG, NLEV, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                            227 * 1024);                                                                          \
-      attr_set = true;                                                                                           \
     }                                                                                                            \
     k_partials_chain<CG, NLEV, METHOD><<<grid, L.threads, L.smem_bytes, stream>>>(dm, sc, bf, L.slots, L.nsplit,  \
                                                                                   force);                        \
@@ -316,20 +317,20 @@ static void launch_tau_chain_cl(const DevModel& dm, const SolverConsts& sc, cons
                                 bool force, cudaStream_t stream) {
   const int threads = 64, groups = threads / CG;  // 2560 (b,t) items x CG lanes: small CTAs reach every SM
   const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv, 1) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_tau_chain<CG, NLEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(k_tau_chain<CG, NLEV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    attr_set = true;
   }
   g_launch_counter += 1;
   const TrajBuf& tb = scratch ? bf.sc : bf.st;
   const int grid = (sc.B * sc.T + groups - 1) / groups;
   if (bf.stash)
     k_tau_chain<CG, NLEV, true><<<grid, threads, smem, stream>>>(dm, sc, tb, bf.stash, bf.stash_half, scratch ? 1 : 0,
-                                                                 bf.ctl, force);
+                                                                 bf.ctl, force, scratch ? nullptr : bf.act_base);
   else
-    k_tau_chain<CG, NLEV><<<grid, threads, smem, stream>>>(dm, sc, tb, nullptr, 0, 0, bf.ctl, force);
+    k_tau_chain<CG, NLEV><<<grid, threads, smem, stream>>>(dm, sc, tb, nullptr, 0, 0, bf.ctl, force,
+                                                           scratch ? nullptr : bf.act_base);
 }
 
 // Instantiated (lanes per evaluation, padded tree depth) pairs; anything else falls back to the

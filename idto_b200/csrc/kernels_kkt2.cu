@@ -633,10 +633,9 @@ static void launch_tw2_kb(const SolverConsts& sc, const SolverBufs& bf, bool for
   constexpr int LD = (KB + 1) & ~1, kl = KB * LD;
   const int sweep = 19 * kl + 6 * LD + kLuWarps * KB * 32 + kLuWarps * 2 * (KB + (2 * KB + 1 + kLuWarps - 1) / kLuWarps + 1), tail = std::max(2 * KB * (2 * KB + 1) + 2 + 8 * KB * KB + 4 * KB, 3 * (2 * KB * KB + LD) + 2 * LD);
   const int smem = std::max(sweep, tail) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_kkt_tw2<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
   }
   k_kkt_tw2<KB><<<2 * sc.B, kThreads, smem, stream>>>(sc, bf, force ? 1 : 0);
 }

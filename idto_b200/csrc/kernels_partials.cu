@@ -246,10 +246,9 @@ template <int G, int METHOD>
 static void launch_partials_gm(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
                                cudaStream_t stream) {
   const PartialsLayout L = partials_layout(dm, sc.nq);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_partials<G, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
   }
   const int grid = (sc.B * sc.T + L.slots - 1) / L.slots;
   g_launch_counter += 1;

@@ -68,7 +68,7 @@ template <int MODE>
 __device__ __forceinline__ void path_eval(const GModel& M, const SolverConsts& sc, const PathPlan& pl,
                                           const double* __restrict__ st, const double* __restrict__ q,
                                           const double* __restrict__ v, const double* __restrict__ a,
-                                          const Perturb& pt, double* rows) {
+                                          const Perturb& pt, double* rows, int* act_out = nullptr) {
   constexpr bool kPose = MODE == kEvalFull;
   constexpr bool kBias = MODE == kEvalFull || MODE == kEvalSharedPose;
   // ---- outward pass over the subtree chain ----------------------------------------------------------------
@@ -193,6 +193,7 @@ __device__ __forceinline__ void path_eval(const GModel& M, const SolverConsts& s
           const double exponent = -distance / sc.sigma;
           fn_c = exponent >= 37 ? -sc.k * distance : sc.sigma * sc.k * log(1 + exp(exponent));
         }
+        if (act_out) act_out[ip] = fn_c > 0.0 ? 1 : 0;  // debug trace (idto_debug_pair_trace)
         if (!(fn_c > 0.0)) continue;
         const V3 nhat = -nhat_BA_W;
         const V3 p_WC = 0.5 * ((mul(R_WGa, p_ACa) + p_WGa) + (mul(R_WGb, p_BCb) + p_WGb));
@@ -348,7 +349,9 @@ __global__ void __launch_bounds__(128) k_partials_path(DevModel dm, SolverConsts
   const double m = ((kk & 1) ? -1.0 : 1.0) * ((kk >= 2) ? 2.0 : 1.0);  // this lane's stencil point
   if (phase == 0) {  // A: tau[t-1] = ID(q_t^e, v_t^e, a_{t-1}^e)   (cc:526-531, 763-787)
     pt.dq = m * dq, pt.cv = m * dv, pt.ca = m * da, pt.uv = 1.0, pt.ua = 1.0;
-    path_eval<kEvalFull>(M, sc, pl, rec_of(t - 1), qB + size_t(t) * nq, vB + size_t(t) * nv, aB + size_t(t - 1) * nv, pt, R0);
+    int* act = bf.act_fd ? bf.act_fd + ((((size_t(b) * T + (t - 1)) * nq + i) * 4 + kk) * dm.np) : nullptr;
+    path_eval<kEvalFull>(M, sc, pl, rec_of(t - 1), qB + size_t(t) * nq, vB + size_t(t) * nv, aB + size_t(t - 1) * nv, pt, R0,
+                         act);
     dst = bf.dqp + (size_t(b) * T + (t - 1)) * nv * nq;
     tau_base = bf.st.tau + (size_t(b) * T + (t - 1)) * nv;
   } else if (phase == 1) {  // B: tau[t] = ID(q_{t+1}, v_{t+1}^e, a_t^e)   (cc:533-540, 788-814)

@@ -260,21 +260,22 @@ __global__ void __launch_bounds__(256) k_kkt_solve(SolverConsts sc, SolverBufs b
 template <int KB>
 static void launch_kkt_kb(const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
   const int smem = (6 * KB * KB + KB * (3 * KB + 1) + 2 * KB) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_kkt_solve<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   k_kkt_solve<KB><<<sc.B, 256, smem, stream>>>(sc, bf, force ? 1 : 0);
 }
 
 template <int KB>
-static void launch_kkt_dispatch(int kb, const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
+static bool launch_kkt_dispatch(int kb, const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
   if (kb == KB) {
     launch_kkt_kb<KB>(sc, bf, force, stream);
+    return true;
   } else if constexpr (KB < 32) {
-    launch_kkt_dispatch<KB + 1>(kb, sc, bf, force, stream);
+    return launch_kkt_dispatch<KB + 1>(kb, sc, bf, force, stream);
   }
+  return false;
 }
 
 // ---- two-sided ("twisted") block elimination: a cluster of two CTAs per problem ---------------------
@@ -639,23 +640,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
 template <int KB>
 static void launch_kkt_twisted_kb(const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
   const int smem = std::max((6 * KB * KB + KB * (3 * KB + 1) + 2 * KB), 2 * KB * (2 * KB + 1)) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_kkt_twisted<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   k_kkt_twisted<KB><<<2 * sc.B, 256, smem, stream>>>(sc, bf, force ? 1 : 0);
 }
 
 template <int KB>
-static void launch_kkt_twisted_dispatch(int kb, const SolverConsts& sc, const SolverBufs& bf, bool force,
+static bool launch_kkt_twisted_dispatch(int kb, const SolverConsts& sc, const SolverBufs& bf, bool force,
                                         cudaStream_t stream) {
   if (kb == KB) {
     launch_kkt_twisted_kb<KB>(sc, bf, force, stream);
+    return true;
   } else if constexpr (KB < 32) {
-    launch_kkt_twisted_dispatch<KB + 1>(kb, sc, bf, force, stream);
+    return launch_kkt_twisted_dispatch<KB + 1>(kb, sc, bf, force, stream);
   }
+  return false;
 }
+
+// No KKT kernel exists for this block size (idto_solver_create rejects such models; this is the backstop):
+// raise the sticky status so that the call fails instead of consuming a stale solution.
+__global__ void k_kkt_unsupported(int* status) { atomicExch(status, IDTO_ERR_UNSUPPORTED); }
 
 void launch_factor(const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
   (void)sc, (void)bf, (void)force, (void)stream;  // fused into launch_lagrange (k_kkt_solve)
@@ -667,11 +673,12 @@ void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBuf
   const int kb = sc.nq + (sc.eq ? sc.nu : 0);
   g_launch_counter += 1;
   // two-sided elimination needs at least 4 block rows per half to pay off; 2*kb interface unknowns must fit n
-  if (sc.linear_solver != IDTO_LINSOLVE_THOMAS && sc.T + 1 >= 8) {
-    if (!launch_kkt_tw2(kb, sc, bf, force, stream)) launch_kkt_twisted_dispatch<1>(kb, sc, bf, force, stream);
-  }
+  bool launched;
+  if (sc.linear_solver != IDTO_LINSOLVE_THOMAS && sc.T + 1 >= 8)
+    launched = launch_kkt_tw2(kb, sc, bf, force, stream) || launch_kkt_twisted_dispatch<1>(kb, sc, bf, force, stream);
   else
-    launch_kkt_dispatch<1>(kb, sc, bf, force, stream);
+    launched = launch_kkt_dispatch<1>(kb, sc, bf, force, stream);
+  if (!launched) k_kkt_unsupported<<<1, 1, 0, stream>>>(bf.status);
   launch_gm_matvec(sc, bf, force, stream);  // gm, merit, gHg, g.g
 }
 

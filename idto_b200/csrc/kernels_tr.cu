@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(kRowThreads) k_trust_update(SolverConsts sc, S
       ctl->derivs_dirty = 0;
     }
     double Delta = ctl->Delta;
+    ctl->Delta_prev = Delta;
     if (rho < 0.25)
       Delta *= 0.25;
     else if (rho > 0.75 && ctl->tr_active)
@@ -374,7 +375,12 @@ __global__ void __launch_bounds__(256) k_conv_check(SolverConsts sc, SolverBufs 
     ctl->prev_cost = cost;
     ctl->reason = reason;
     ctl->pending = 0;
-    if (reason != 0) ctl->active = 0;
+    if (reason != 0) {
+      ctl->active = 0;
+      // the reference leaves its loop BEFORE the trust-region update of a converged step (cc:2608-2622); that
+      // update already ran here (the check needs the next derivative pipeline): undo it
+      ctl->Delta = ctl->Delta_prev;
+    }
   }
 }
 
@@ -395,11 +401,10 @@ void launch_clear_dirty(const SolverConsts& sc, const SolverBufs& bf, cudaStream
 void launch_gm_matvec(const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
   g_launch_counter += 1;
   const int smem = 5 * sc.nq * sc.nq * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_gm_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_trust_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
   }
   k_gm_matvec<<<sc.B*(sc.T + 1), kRowThreads, smem, stream>>>(sc, bf, force ? 1 : 0);
 }
@@ -413,10 +418,9 @@ void launch_trust_update(const DevModel& dm, const SolverConsts& sc, const Solve
                          cudaStream_t stream) {
   (void)dm;
   g_launch_counter += 1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_trust_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
   }
   k_trust_update<<<sc.B*(sc.T + 1), kRowThreads, 5 * sc.nq * sc.nq * 8, stream>>>(sc, bf, commit ? 1 : 0);
 }

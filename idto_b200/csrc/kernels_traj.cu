@@ -182,10 +182,9 @@ static void launch_tau_g(const DevModel& dm, const SolverConsts& sc, const TrajB
                          bool force, cudaStream_t stream) {
   const int threads = 128, groups = threads / G;
   const int smem = model_smem_bytes(dm) + groups * (pos_smem_doubles(dm) + vel_smem_doubles(dm)) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_tau<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   const int grid = (sc.B * sc.T + groups - 1) / groups;
   g_launch_counter += 1;

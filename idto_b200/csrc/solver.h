@@ -82,6 +82,7 @@ struct TrajBuf {
 // Per-problem trust-region control block (device resident; host never reads it mid-solve).
 struct ProbCtl {
   double Delta, rho, prev_cost, merit, cost_kp, gnorm, hnorm, dq_norm, dqH_norm, q_norm, dL_dq;
+  double Delta_prev;  // Delta before the last update: restored when that step turns out to have converged (cc:2601-2622)
   int traj_dirty;    // q changed: v, a, tau, cost, h stale
   int derivs_dirty;  // partials / g / H / D / factor / lambda stale
   int active;        // still iterating (not converged)
@@ -112,6 +113,11 @@ struct SolverBufs {
   double* stats;  // [B][stats_cap][IDTO_NUM_STATS]
   int stats_cap;
   int* status;  // [1] sticky device-side error flag (factorisation failure, active-pair overflow)
+  // Debug trace of the contact pairs each inverse-dynamics evaluation applies forces for (idto_debug_pair_trace;
+  // null otherwise): act_base [B][T][np] for tau_t of the state trajectory, act_fd [B][T][nq][4][np] for the
+  // perturbed evaluations of tau_{t-1} at q_t +- dq e_i (stencil point kk = 0..3: +dq, -dq, +2dq, -2dq), -1 where
+  // an evaluation did not visit the pair (path columns: pairs outside the owner's subtree keep the base forces).
+  int *act_base, *act_fd;
 };
 
 // ---- kernel launchers (each in its own .cu; all asynchronous on `stream`) ---------------------

@@ -201,8 +201,9 @@ def SetSolverParameters(options: TrajOptExampleParams) -> SolverParameters:
         smoothing_factor=float(options.smoothing_factor), scaling=bool(options.scaling),
         scaling_method=sm[options.scaling_method], equality_constraints=bool(options.equality_constraints),
         Delta0=float(options.Delta0), Delta_max=float(options.Delta_max), num_threads=int(options.num_threads),
-        convergence_tolerances=t,
-        check_convergence=any(getattr(t, f.name) != 0.0 for f in fields(ConvergenceCriteriaTolerances)))
+        convergence_tolerances=t)
+    # check_convergence keeps its default (False): the reference's SetSolverParameters copies the tolerances
+    # (example_base.cc:427-543) and never enables the check; only its unit tests do
     # recorded for the caller; anything outside the CUDA hot path is rejected at solver creation
     p.unsupported = [name for name, bad in (("method: linesearch", options.method == "linesearch"),
                                             ("gradients_method: autodiff", options.gradients_method == "autodiff"),

@@ -135,7 +135,11 @@ int idto_model_num_unactuated(idto_model_t m);
 /* out[num_unactuated]: velocity indices of unactuated dofs (trajectory_optimizer.cc:63-72). */
 int idto_model_unactuated_dofs(idto_model_t m, int* out);
 
-/* A solver = one TrajectoryOptimizer bound to `batch` independent WarmStarts
+/* A solver lives on the device that was current when its model was created; every entry point taking a
+ * solver makes that device current for the calling thread (one host thread per device may drive several
+ * solvers concurrently; one solver is not re-entrant, like the reference's TrajectoryOptimizer).
+ *
+ * A solver = one TrajectoryOptimizer bound to `batch` independent WarmStarts
  * (state + scratch_state + Delta + dq + dqH, optimizer/warm_start.h:23-76),
  * all device resident.  `prob` is the template problem; per-batch-element
  * q_init/v_init/q_nom/v_nom are set with the calls below. */
@@ -182,6 +186,9 @@ int idto_eval_trust_ratio(idto_solver_t s);
  * `out` must hold idto_field_size(field) * batch doubles.  Names:
  *  q v a tau Nplus cost h dtau_dqm dtau_dqt dtau_dqp g H_A H_B H_C D Hs_A Hs_B Hs_C gs
  *  J lambda merit gm dq dqH dq_active rho delta q_nom v_nom
+ *  dvt_dqt dvt_dqm  (EvalVelocityPartials, velocity_partials.h:19-39: +N+_t/dt, -N+_t/dt with [0] = NaN;
+ *                    never materialised on the device, formed on the host from Nplus)
+ *  pair_active pair_active_fd  (only after idto_debug_pair_trace, see below)
  * Layouts follow the reference containers: per time step, column-major blocks. */
 long idto_field_size(idto_solver_t s, const char* field);
 int idto_get(idto_solver_t s, const char* field, double* out);
@@ -202,7 +209,10 @@ int idto_solve(idto_solver_t s, int max_iterations, int* iters_out, int* reason_
  * buffers: H2D of the guess/initial conditions, the iterations, and D2H of the
  * solution are all enqueued; call idto_synchronize() to wait.  This is the
  * end-to-end MPC re-solve call (examples/mpc_controller.cc:43-85).
- * Any input pointer may be NULL to keep the device-resident value. */
+ * Any input pointer may be NULL to keep the device-resident value.
+ * iters_out (pinned host [batch], may be NULL) receives the number of iterations recorded per problem:
+ * with check_convergence a problem may stop early, and rows of stats_out beyond iters_out[b] are not
+ * written by this call. */
 int idto_resolve_async(idto_solver_t s, int max_iterations,
                        const double* q_guess, const double* q_init, const double* v_init,
                        const double* q_nom, const double* v_nom,
@@ -227,6 +237,17 @@ int idto_fence(idto_solver_t s);
 /* Benchmark hygiene: overwrite `bytes` of caller-provided device scratch (larger than L2) in the
  * solver's stream order, so that the next re-solve starts with a cold L2. */
 int idto_flush_l2(idto_solver_t s, void* scratch, size_t bytes);
+
+/* Debug trace of the contact-pair indexing (trajectory_optimizer.cc:272-279: the pairs
+ * ComputeSignedDistancePairwiseClosestPoints(threshold) returns are the ones a force is computed for).
+ * After enabling, the inverse-dynamics kernels record which candidate pairs each evaluation applies a
+ * force for, and idto_get serves
+ *   "pair_active"    [batch][T][npairs]        tau_t of the current trajectory: 1 = force computed, 0 = not
+ *   "pair_active_fd" [batch][T][nq][4][npairs] the perturbed evaluations of tau_{t-1} at q_t + m dq e_i, stencil
+ *                    point m = +1, -1, +2, -2 (the ones the gradients_method uses); -1 = the evaluation did not
+ *                    visit the pair (subtree-only evaluations keep the base force of pairs outside the subtree)
+ * (as doubles).  Tracing forces every evaluation to run and disables the sub-batch streams: debugging only. */
+int idto_debug_pair_trace(idto_solver_t s, int enable);
 
 /* Number of kernel launches issued by this solver since creation. */
 long idto_launch_count(idto_solver_t s);

@@ -50,7 +50,8 @@ def test_inline_yaml_defaults_and_mapping():
     p = yaml_config.SetSolverParameters(o)
     assert p.gradients_method == GRAD_CENTRAL and p.max_iterations == 7 and p.Delta0 == 1e-3
     assert p.scaling and p.scaling_method == SCALING_DOUBLE_SQRT and p.equality_constraints
-    assert p.check_convergence and p.convergence_tolerances.rel_cost_reduction == 1e-6
+    # tolerances are copied, the check itself stays off (example_base.cc:427-543 never sets check_convergence)
+    assert not p.check_convergence and p.convergence_tolerances.rel_cost_reduction == 1e-6
     assert p.q_nom_relative_to_q_init.tolist() == [False, True, False, False, False] and p.unsupported == []
     g = yaml_config.MakeInitialGuess(o)
     assert len(g) == 11 and np.allclose(g[0], o.q_init) and np.allclose(g[-1], o.q_guess)
