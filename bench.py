@@ -35,12 +35,21 @@ from idto_b200 import problems  # noqa: E402
 from idto_b200.types import GRAD_CENTRAL, GRAD_FORWARD, NUM_STATS  # noqa: E402
 
 BATCH = 64
-T = 40
 METRIC = "Gauss-Newton iters/sec, Mini Cheetah T=40"
+# name -> (problems.<fn>, BASELINE horizon, description); mini_cheetah is the configuration the metric is quoted on,
+# the others are BASELINE.json's other configs (driver-timed lines for them: --workload)
+WORKLOADS = {
+    "mini_cheetah": ("mini_cheetah", 40, "mini_cheetah trot (floating base + 12 DOF, 4 foot-ground pairs)"),
+    "allegro_hand": ("allegro_hand", 60, "allegro_hand in-hand sphere rotation (16 finger joints + free ball, 188 "
+                                         "candidate contact pairs)"),
+    "hopper": ("hopper", 50, "hopper planar contact (planar base + 2 joints, 2 foot-ground pairs)"),
+    "spinner": ("spinner", 40, "spinner (2-link finger + spinner, 1 sphere-sphere pair)"),
+}
 
 
-def workload(method):
-    m, dt, prob, params, guess = problems.mini_cheetah(T=T, gradients_method=method, max_iterations=1)
+def workload(method, name="mini_cheetah"):
+    fn, T, _ = WORKLOADS[name]
+    m, dt, prob, params, guess = getattr(problems, fn)(T=T, gradients_method=method, max_iterations=1)
     return m, dt, prob, params
 
 
@@ -65,7 +74,7 @@ class ClockSampler:
             if probe.returncode != 0 or "not a valid" in (probe.stdout + probe.stderr).lower():
                 self.Q = self.Q.replace("clocks_event_reasons", "clocks_throttle_reasons")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -89,14 +98,14 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_arm(method, steps, warmup, nprob=BATCH, cores=None):
+def cpu_arm(method, steps, warmup, nprob=BATCH, cores=None, name="mini_cheetah"):
     """The reference's CPU path (restated: oracle/idto_oracle.cc — Drake is not installable, so this is
     'kind: port').  Independent optimizers run on independent host threads (the reference's threading
     contract), one WarmStart each, OpenMP off inside (every core already has a problem)."""
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import oracle
-    m, dt, prob, params = workload(method)
+    m, dt, prob, params = workload(method, name)
     cores = cores or os.cpu_count() or 1
     nthreads = min(cores, nprob)
     omp = max(1, cores // nprob)  # spare cores go to the reference's own OpenMP loops over t (cc:214, 455)
@@ -131,7 +140,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="idto_b200", choices=["idto_b200", "reference"])
     ap.add_argument("--method", default="central", choices=["central", "forward"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--batch", type=int, default=BATCH, help="problems per GPU (weak) or in the whole job (strong)")
+    ap.add_argument("--workload", default="mini_cheetah", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch problems per GPU; strong: --batch problems split over the GPUs "
+                         "(BASELINE config 4: 'batch=64 MPC solves across 1/2/4/8 GPUs')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     method = GRAD_CENTRAL if args.method == "central" else GRAD_FORWARD
@@ -139,20 +152,34 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(args.warmup, 3)
-    m, dt, prob, params = workload(method)
-    config = {"workload": f"mini_cheetah trot (floating base + 12 DOF, 4 foot-ground pairs), T={T}, "
-                          f"batch={args.batch} independent MPC re-solves per GPU, 1 iteration per step, "
-                          f"gradients={args.method}_differences, equality_constraints=on, scaling=double_sqrt",
-              "urdf": "mini_cheetah_with_ground", "nq": m.nq, "nv": m.nv, "T": T, "batch_per_gpu": args.batch,
-              "l2": "flushed before every step (160 MiB memset in stream order, inside the timed region; L2 = 126 MB)"}
+    m, dt, prob, params = workload(method, args.workload)
+    T = WORKLOADS[args.workload][1]
+    metric = METRIC if args.workload == "mini_cheetah" else f"Gauss-Newton iters/sec, {args.workload} T={T}"
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit(f"bench.py: --scaling strong needs --batch ({args.batch}) divisible by the GPU count ({world})")
+        B = args.batch // world
+    else:
+        B = args.batch
+    config = {"workload": f"{WORKLOADS[args.workload][2]}, T={T}, "
+                          + (f"batch={args.batch} independent MPC re-solves per GPU" if args.scaling == "weak" else
+                             f"batch={args.batch} independent MPC re-solves in the whole job, {B} per GPU")
+                          + f", 1 iteration per step, gradients={args.method}_differences, equality_constraints=on, "
+                            "scaling=double_sqrt",
+              "model": m.name, "nq": m.nq, "nv": m.nv, "T": T, "batch_per_gpu": B, "global_batch": B * world,
+              "l2": "flushed before every step: a 160 MiB memset (L2 = 126 MB) on the solver's stream, ordered after "
+                    "the previous step and before the next on every internal stream, inside the timed region"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        val, ms, cores, sample = cpu_arm(method, max(1, min(args.steps, 5)), 1, nprob=args.batch)
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "iters/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        # every step is one iteration of each of the --batch problems (the whole workload of one GPU step: it is
+        # small enough on the host, ~0.1-0.3 s, that the sample is not cut down); exactly --steps / --warmup are run
+        ref_warmup = max(args.warmup, 1)
+        val, ms, cores, sample = cpu_arm(method, max(1, args.steps), ref_warmup, nprob=args.batch, name=args.workload)
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": "iters/s", "n_gpus": args.gpus,
+                "steps": max(1, args.steps), "warmup": ref_warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -166,7 +193,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B = args.batch
     model = capi.Model(m)
     gs = capi.BatchSolver(model, dt, prob, params, B)
     # batch element b of rank r is problem r*B + b of the global job
@@ -195,12 +221,14 @@ def main():
         gs.invalidate()
         gs.resolve_async(1)  # no host pointers: everything stays in HBM, nothing synchronises
 
+    # clocks / throttle reasons are sampled every 20 ms from the warm-up to the end of the end-to-end region (the
+    # timed regions sit inside that window, back to back, all of it under load)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(warmup):
         step_resident()
-    sampler = ClockSampler(local_rank)
     gs.fence()
     barrier()
-    sampler.start()
     l0 = gs.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -210,7 +238,6 @@ def main():
     e1.record()
     barrier()
     launches = gs.launch_count() - l0
-    clocks = sampler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -247,6 +274,7 @@ def main():
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(el.item())
+    clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel (ID partials), CUDA events on the launching stream --------
     gs.profile_enable(True)
@@ -272,13 +300,28 @@ def main():
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             prof = json.load(f)
-        traffic = prof.get(f"id_partials_{args.method}")
-        flop = prof.get(f"id_partials_{args.method}_fp64_flop")
+        key = f"id_partials_{args.method}" if args.workload == "mini_cheetah" and B == BATCH else "none"
+        traffic = prof.get(key)
+        flop = prof.get(f"{key}_fp64_flop")
         if flop:  # what actually binds this stage: fp64 issue, not HBM
             fp64 = {"flop_per_launch": flop, "achieved_tflops": flop / (stage_ms["id_partials"] * 1e-3) / 1e12,
                     "peak_tflops": 148 * 64 * 2 * 1.965e9 / 1e12, "source": "ncu instruction counts, profiles/ncu_traffic.json"}
     except OSError:
         pass
+    # The stage that dominates the step is the KKT sweep (lagrange): its roof is neither HBM nor flops but the serial
+    # pivot chain; reported against the fp64 peak with the flops the reference's block recurrence needs
+    # (penta_diagonal_solver.h:124-248 on blocks of kb = nq + nu: per block row one LU (2/3 kb^3), two kb^3
+    # triangular solve pairs for Y and Z and three kb x kb products for K, G: ~ (2/3 + 2*2 + 3*2) kb^3).
+    kb = m.nq + (len(m.unactuated_dofs) if params.equality_constraints else 0)
+    kkt_flop = B * (T + 1) * (2.0 / 3 + 4 + 6) * kb ** 3
+    fp64_peak = 148 * 64 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+    kkt_ms = stage_ms["lagrange"]
+    roofline_kkt = {"kernel": "lagrange stage: KKT sweep (k_kkt_*) + k_gm_matvec", "bound": "fp64 (latency of the serial "
+                    "pivot chain in practice)", "achieved": kkt_flop / (kkt_ms * 1e-3) / 1e12 if kkt_ms > 0 else None,
+                    "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": kkt_flop / (kkt_ms * 1e-3) / 1e12 / fp64_peak if kkt_ms > 0 else None,
+                    "algorithmic_flop_per_launch": kkt_flop, "avg_launch_ms": kkt_ms, "block_size": kb,
+                    "peak_source": "148 SMs x 64 fp64 FMA/clk x 2 x sm_max_mhz"}
     roofline = {"kernel": "id_partials stage: k_partials_path + k_partials_chain", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
                 "avg_launch_ms": stage_ms["id_partials"],
@@ -288,13 +331,14 @@ def main():
                 "stage_ms": stage_ms, "fp64": fp64}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
-                "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        line = {"metric": metric, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches), "roofline": roofline}
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_kkt": roofline_kkt}
         if world == 1 and not args.no_cpu_baseline:
-            val, cms, cores, sample = cpu_arm(method, 2, 1, nprob=B)
+            val, cms, cores, sample = cpu_arm(method, 2, 1, nprob=B, name=args.workload)
             line["cpu_baseline"] = {"value": val, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample,
                                     "ms_per_step": cms}
         print(json.dumps(line))

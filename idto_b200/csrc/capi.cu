@@ -1207,13 +1207,9 @@ int idto_fence(idto_solver_t s) {
 int idto_flush_l2(idto_solver_t s, void* scratch, size_t bytes) {
   if (!s || !scratch) return IDTO_ERR_INVALID_ARG;
   cudaSetDevice(s->device);  // the caller may have changed the current device since creation
-  if (multi(s)) {
-    use_subs(s);
-    const size_t share = bytes / s->nsub;
-    for (int i = 0; i < s->nsub; ++i)
-      IDTO_CUDA_CHECK(cudaMemsetAsync(static_cast<char*>(scratch) + share * i, 0, share, s->sub_streams[i]));
-    return IDTO_OK;
-  }
+  // One memset of the whole scratch on the caller's stream: use_main() orders it after everything the sub-batch
+  // streams hold, and the next sub-stream work forks after it — every step starts with a cold L2 on all streams
+  // (per-sub-stream partial memsets, the first version, left up to half of the L2 warm).
   use_main(s);
   IDTO_CUDA_CHECK(cudaMemsetAsync(scratch, 0, bytes, s->stream));
   return IDTO_OK;
