@@ -675,7 +675,8 @@ void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBuf
   // two-sided elimination needs at least 4 block rows per half to pay off; 2*kb interface unknowns must fit n
   bool launched;
   if (sc.linear_solver != IDTO_LINSOLVE_THOMAS && sc.T + 1 >= 8)
-    launched = launch_kkt_tw2(kb, sc, bf, force, stream) || launch_kkt_twisted_dispatch<1>(kb, sc, bf, force, stream);
+    launched = launch_kkt_v3(kb, sc, bf, force, stream) || launch_kkt_tw2(kb, sc, bf, force, stream) ||
+               launch_kkt_twisted_dispatch<1>(kb, sc, bf, force, stream);
   else
     launched = launch_kkt_dispatch<1>(kb, sc, bf, force, stream);
   if (!launched) k_kkt_unsupported<<<1, 1, 0, stream>>>(bf.status);

@@ -134,6 +134,8 @@ void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBuf
                      cudaStream_t stream);
 // register-resident two-sided KKT sweep (kernels_kkt2.cu); false if this block size is not instantiated
 bool launch_kkt_tw2(int kb, const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
+// third generation (kernels_kkt3.cu): single-warp LU + column-per-thread triangular solves; same contract
+bool launch_kkt_v3(int kb, const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
 void launch_conv_check(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
 void launch_clear_dirty(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
 void launch_gm_matvec(const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
