@@ -48,6 +48,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         H = ctypes.c_void_p
         L.idto_last_error.restype = ctypes.c_char_p
+        L.idto_set_device.argtypes = [ctypes.c_int]
         L.idto_params_default.argtypes = [ctypes.POINTER(Params)]
         L.idto_model_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.POINTER(H)]
         L.idto_model_destroy.argtypes = [H]
@@ -96,6 +97,11 @@ def _p(a):
 
 def device_count():
     return lib().idto_device_count()
+
+
+def set_device(device: int):
+    """Make CUDA device `device` current for the calling thread (models bind to the current device)."""
+    _check(lib().idto_set_device(int(device)))
 
 
 class Model:
@@ -244,3 +250,50 @@ class BatchSolver:
         n = ctypes.c_long(0)
         _check(lib().idto_profile_read(self.h, name.encode(), ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+
+class MultiDeviceBatchSolver:
+    """`batch` independent WarmStarts spread over the GPUs of this process: one Model + BatchSolver per device,
+    one host thread per device for every call (ctypes releases the GIL), contiguous batch slices, no collective
+    (SURVEY.md 8e).  The in-process twin of `torchrun bench.py --gpus N`; arrays are indexed by GLOBAL problem."""
+
+    def __init__(self, baked: BakedModel, time_step, prob, params, batch, devices=None):
+        from concurrent.futures import ThreadPoolExecutor
+
+        from .sharding import shard_slice
+        n = device_count()
+        if n == 0:
+            raise IdtoError("idto_b200: no CUDA device (no CPU fallback)")
+        self.devices = list(range(n)) if devices is None else list(devices)
+        self.devices = self.devices[:max(1, min(len(self.devices), int(batch)))]
+        self.B, self.T, self.nq, self.nv = int(batch), prob.num_steps, baked.nq, baked.nv
+        self.slices = [shard_slice(self.B, r, len(self.devices)) for r in range(len(self.devices))]
+        self._pool = ThreadPoolExecutor(len(self.devices))
+
+        def make(r):
+            set_device(self.devices[r])
+            sl = self.slices[r]
+            return BatchSolver(Model(baked), time_step, prob, params, sl.stop - sl.start)
+        self.shards = list(self._pool.map(make, range(len(self.devices))))
+
+    def _each(self, fn):
+        return list(self._pool.map(lambda r: fn(self.shards[r], self.slices[r]), range(len(self.shards))))
+
+    def set_q(self, q):
+        q = np.asarray(q, float)
+        self._each(lambda s, sl: s.set_q(q[sl] if q.ndim == 3 else q))
+
+    def reset_initial_conditions(self, q0, v0):
+        q0, v0 = np.asarray(q0, float), np.asarray(v0, float)
+        self._each(lambda s, sl: s.reset_initial_conditions(q0[sl], v0[sl]))
+
+    def solve(self, max_iterations):
+        parts = self._each(lambda s, sl: s.solve(max_iterations))
+        return tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+
+    def solution(self):
+        parts = self._each(lambda s, sl: s.solution())
+        return tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+
+    def get(self, name):
+        return np.concatenate(self._each(lambda s, sl: s.get(name)))

@@ -193,6 +193,7 @@ void make_view(const idto_solver_s* s, int b0, int nb, SolverConsts* scv, Solver
   for (double** p : {&v.HA, &v.HB, &v.HC, &v.SA, &v.SB, &v.SC}) *p += o * T1 * nq * nq;
   v.Jm += o * T * nuq, v.Jt += o * T * nuq, v.Jp += o * T * nuq;
   v.FY += o * T1 * kb * kb, v.FZ += o * T1 * kb * kb, v.X += o * T1 * kb, v.rhs += o * nh;
+  if (v.S) v.S += o * n * (3 * nq);
   v.pH += o * n, v.dq += o * n, v.dqH += o * n, v.tmp1 += o * n, v.tmp2 += o * n, v.red += o * 8, v.part += o * T1 * 4, v.cnt += o;
   if (v.stash) v.stash += o * T * size_t(s->model->dm.nb) * 48;
   v.ctl += o;
@@ -365,6 +366,13 @@ int idto_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
   return n;
+}
+
+int idto_set_device(int device) {
+  if (int rc = check_device()) return rc;
+  if (device < 0 || device >= idto_device_count()) return IDTO_ERR_INVALID_ARG;
+  IDTO_CUDA_CHECK(cudaSetDevice(device));
+  return IDTO_OK;
 }
 
 void idto_params_default(idto_params* p) {  // optimizer/solver_parameters.h:64-167
@@ -629,6 +637,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
     set_last_error("only diagonal cost weights are supported by the CUDA path");
     return IDTO_ERR_UNSUPPORTED;
   }
+  if (p->linear_solver < IDTO_LINSOLVE_THOMAS || p->linear_solver > IDTO_LINSOLVE_DENSE_LDLT) return IDTO_ERR_INVALID_ARG;
   if (p->gradients_method < IDTO_GRAD_FORWARD || p->gradients_method > IDTO_GRAD_CENTRAL4) {
     set_last_error("gradients_method must be forward, central or central4 (autodiff needs Drake scalars)");
     return IDTO_ERR_UNSUPPORTED;
@@ -705,6 +714,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   alloc(&bf.Jm, nJ), alloc(&bf.Jt, nJ), alloc(&bf.Jp, nJ);
   const size_t kbm = size_t(nq) + sc.nu;  // KKT block size
   bf.FK = bf.FG = bf.S = nullptr;
+  if (p->linear_solver == IDTO_LINSOLVE_DENSE_LDLT) alloc(&bf.S, size_t(B) * sc.n * (3 * nq));  // band storage of H~
   alloc(&bf.FY, size_t(B) * (T + 1) * kbm * kbm), alloc(&bf.FZ, size_t(B) * (T + 1) * kbm * kbm);
   alloc(&bf.X, size_t(B) * (T + 1) * kbm);
   alloc(&bf.rhs, size_t(B) * nh);

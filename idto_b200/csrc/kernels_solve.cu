@@ -663,6 +663,72 @@ static bool launch_kkt_twisted_dispatch(int kb, const SolverConsts& sc, const So
 // raise the sticky status so that the call fails instead of consuming a stale solution.
 __global__ void k_kkt_unsupported(int* status) { atomicExch(status, IDTO_ERR_UNSUPPORTED); }
 
+
+// ---- SolverParameters::LinearSolverType::kDenseLdlt (cc:2088-2093) ---------------------------------------------
+// The reference's debugging alternative to the block penta-diagonal solver for the Gauss-Newton step:
+// pH = H~.ldlt().solve(-gm / Delta).  Here: an LDL^T factorisation that knows nothing about the block structure
+// (H~ stored as a plain band matrix of half bandwidth 3 nq - 1, one CTA per problem), run AFTER the KKT sweep, whose
+// lambda it keeps; it overwrites x = -H~^-1 gm (= pH Delta).  A cross-check, not a fast path.
+__global__ void __launch_bounds__(256) k_dense_ldlt(SolverConsts sc, SolverBufs bf, int force) {
+  extern __shared__ __align__(16) double xs[];  // [n]
+  __shared__ double s_d;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  if (!force && !bf.ctl[b].derivs_dirty) return;
+  const int nq = sc.nq, n = sc.n, bw = 3 * nq - 1, ld = bw + 1, kk = nq * nq, nblk = sc.T + 1;
+  double* A = bf.S + size_t(b) * n * ld;  // A[i * ld + (i - j)] = H~(i, j), 0 <= i - j <= bw
+  const double* SA = bf.SA + size_t(b) * nblk * kk;
+  const double* SB = bf.SB + size_t(b) * nblk * kk;
+  const double* SC = bf.SC + size_t(b) * nblk * kk;
+  for (int e = tid; e < n * ld; e += nt) {
+    const int i = e / ld, j = i - (e - i * ld);
+    double val = 0.0;
+    if (j >= 0) {
+      const int bi = i / nq, ri = i - bi * nq, bj = j / nq, cj = j - bj * nq, d = bi - bj;
+      const double* blk = d == 0 ? SC : (d == 1 ? SB : (d == 2 ? SA : nullptr));
+      if (blk) val = blk[size_t(bi) * kk + cj * nq + ri];
+    }
+    A[e] = val;
+  }
+  for (int e = tid; e < n; e += nt) xs[e] = -bf.gm[size_t(b) * n + e];
+  __syncthreads();
+  const int ta = tid & 63, tb = tid >> 6;  // row offset, column-offset group (4 groups)
+  for (int k = 0; k < n; ++k) {
+    if (tid == 0) {
+      s_d = A[size_t(k) * ld];
+      if (!(s_d > 0.0)) atomicExch(bf.status, IDTO_ERR_FACTORIZATION);
+    }
+    __syncthreads();
+    const double inv = 1.0 / s_d;
+    const int m = min(bw, n - 1 - k);
+    // trailing update inside the band: A(i, j) -= (A(i, k) / d) A(j, k),  k < j <= i <= k + m
+    for (int a = ta + 1; a <= m; a += 64) {
+      const double lik = A[size_t(k + a) * ld + a] * inv;
+      for (int c = tb + 1; c <= a; c += 4) A[size_t(k + a) * ld + (a - c)] -= lik * A[size_t(k + c) * ld + c];
+    }
+    __syncthreads();
+    for (int a = tid + 1; a <= m; a += nt) A[size_t(k + a) * ld + a] *= inv;  // L(k + a, k)
+  }
+  __syncthreads();
+  // L y = b,  D z = y,  L^T x = z  (axpy forms)
+  for (int k = 0; k < n; ++k) {
+    const double xk = xs[k];
+    const int m = min(bw, n - 1 - k);
+    __syncthreads();
+    for (int a = tid + 1; a <= m; a += nt) xs[k + a] -= A[size_t(k + a) * ld + a] * xk;
+    __syncthreads();
+  }
+  for (int e = tid; e < n; e += nt) xs[e] /= A[size_t(e) * ld];
+  __syncthreads();
+  for (int k = n - 1; k >= 0; --k) {
+    const double xk = xs[k];
+    const int m = min(bw, k);
+    __syncthreads();
+    for (int a = tid + 1; a <= m; a += nt) xs[k - a] -= A[size_t(k) * ld + a] * xk;
+    __syncthreads();
+  }
+  for (int e = tid; e < n; e += nt) bf.pH[size_t(b) * n + e] = xs[e];
+}
+
 void launch_factor(const SolverConsts& sc, const SolverBufs& bf, bool force, cudaStream_t stream) {
   (void)sc, (void)bf, (void)force, (void)stream;  // fused into launch_lagrange (k_kkt_solve)
 }
@@ -681,6 +747,13 @@ void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBuf
     launched = launch_kkt_dispatch<1>(kb, sc, bf, force, stream);
   if (!launched) k_kkt_unsupported<<<1, 1, 0, stream>>>(bf.status);
   launch_gm_matvec(sc, bf, force, stream);  // gm, merit, gHg, g.g
+  if (sc.linear_solver == IDTO_LINSOLVE_DENSE_LDLT && bf.S) {
+    static bool attr_set[kMaxDevices] = {};
+    if (first_use_on_device(attr_set))
+      cudaFuncSetAttribute(k_dense_ldlt, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    g_launch_counter += 1;
+    k_dense_ldlt<<<sc.B, 256, sc.n * sizeof(double), stream>>>(sc, bf, force ? 1 : 0);
+  }
 }
 
 }  // namespace idto

@@ -13,7 +13,7 @@ configs (examples/*/*.yaml) drive the CUDA path unmodified:
     solver.set_q(MakeInitialGuess(opts))
 
 Options that select code outside the hot path (method: linesearch, gradients_method: autodiff,
-linear_solver: dense_ldlt, exact_hessian) parse like in the reference and are recorded on the returned
+exact_hessian) parse like in the reference and are recorded on the returned
 parameters; the CUDA solver rejects them at creation (IDTO_ERR_UNSUPPORTED), it never falls back.
 """
 from __future__ import annotations
@@ -22,7 +22,7 @@ from dataclasses import dataclass, field, fields
 
 import numpy as np
 
-from .types import (GRAD_CENTRAL, GRAD_CENTRAL4, GRAD_FORWARD, SCALING_ADAPTIVE_DOUBLE_SQRT, SCALING_ADAPTIVE_SQRT,
+from .types import (LINSOLVE_DENSE_LDLT, LINSOLVE_TWISTED, GRAD_CENTRAL, GRAD_CENTRAL4, GRAD_FORWARD, SCALING_ADAPTIVE_DOUBLE_SQRT, SCALING_ADAPTIVE_SQRT,
                     SCALING_DOUBLE_SQRT, SCALING_SQRT, ConvergenceCriteriaTolerances, ProblemDefinition,
                     SolverParameters)
 
@@ -201,13 +201,13 @@ def SetSolverParameters(options: TrajOptExampleParams) -> SolverParameters:
         smoothing_factor=float(options.smoothing_factor), scaling=bool(options.scaling),
         scaling_method=sm[options.scaling_method], equality_constraints=bool(options.equality_constraints),
         Delta0=float(options.Delta0), Delta_max=float(options.Delta_max), num_threads=int(options.num_threads),
+        linear_solver=LINSOLVE_DENSE_LDLT if options.linear_solver == "dense_ldlt" else LINSOLVE_TWISTED,
         convergence_tolerances=t)
     # check_convergence keeps its default (False): the reference's SetSolverParameters copies the tolerances
     # (example_base.cc:427-543) and never enables the check; only its unit tests do
     # recorded for the caller; anything outside the CUDA hot path is rejected at solver creation
     p.unsupported = [name for name, bad in (("method: linesearch", options.method == "linesearch"),
                                             ("gradients_method: autodiff", options.gradients_method == "autodiff"),
-                                            ("linear_solver: dense_ldlt", options.linear_solver == "dense_ldlt"),
                                             ("exact_hessian", bool(options.exact_hessian))) if bad]
     p.q_nom_relative_to_q_init = _relative(options)
     return p

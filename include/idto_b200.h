@@ -94,7 +94,10 @@ enum { IDTO_GRAD_FORWARD = 0, IDTO_GRAD_CENTRAL = 1, IDTO_GRAD_CENTRAL4 = 2 };
 enum { IDTO_SCALING_SQRT = 0, IDTO_SCALING_ADAPTIVE_SQRT = 1,
        IDTO_SCALING_DOUBLE_SQRT = 2, IDTO_SCALING_ADAPTIVE_DOUBLE_SQRT = 3 };
 /* single top-down block-Thomas sweep, or two-sided ("twisted") elimination by a 2-CTA cluster */
-enum { IDTO_LINSOLVE_THOMAS = 0, IDTO_LINSOLVE_TWISTED = 1 };
+/* TWISTED / THOMAS: the block penta-diagonal solver (reference: kPentaDiagonalLu) as a two-sided or a single
+ * top-down sweep; DENSE_LDLT: the reference's debugging cross-check kDenseLdlt (trajectory_optimizer.cc:2088-2093):
+ * the Gauss-Newton step is re-solved by a structure-agnostic LDL^T of H~. */
+enum { IDTO_LINSOLVE_THOMAS = 0, IDTO_LINSOLVE_TWISTED = 1, IDTO_LINSOLVE_DENSE_LDLT = 2 };
 
 typedef struct {
   int max_iterations;         /* 100 */
@@ -126,6 +129,10 @@ typedef struct idto_solver_s* idto_solver_t;
 
 const char* idto_last_error(void);
 int idto_device_count(void);
+/* Makes CUDA device `device` current for the calling thread (models are created on the current device): lets a
+ * host program without the CUDA runtime headers drive one solver per GPU (one host thread + stream
+ * per device, no collective). */
+int idto_set_device(int device);
 
 /* Copies the tables to the current device.  Replaces the one-time plant query
  * in the TrajectoryOptimizer constructor (trajectory_optimizer.cc:43-72). */

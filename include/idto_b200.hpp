@@ -15,6 +15,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "idto_b200.h"
@@ -182,6 +183,44 @@ struct TrajectoryOptimizerStats {
 // ---- MultibodyPlant stand-in: baked tables (idto_b200/bake.py `save_txt`) + discrete time step ----------
 class MultibodyPlant {
  public:
+  // The baked tables as plain vectors (field names and layouts of idto_model_desc, include/idto_b200.h): what
+  // idto_b200/bake.py writes from URDF / SDF and what BakeFromPlant (idto_b200_drake.hpp) fills from a Drake plant.
+  struct Tables {
+    int nq{0}, nv{0};
+    std::vector<int> parent, joint_type, q_start, v_start, actuated, geom_body, geom_type, pair_geomA, pair_geomB;
+    std::vector<double> X_PF, R_MB, axis, damping, mass, com, inertia, gravity, geom_dims, X_BG;
+  };
+  static MultibodyPlant FromTables(const Tables& t, double time_step) {
+    MultibodyPlant p;
+    p.dt_ = time_step;
+    const int nb = int(t.parent.size()), ng = int(t.geom_body.size()), np = int(t.pair_geomA.size());
+    if (int(t.joint_type.size()) != nb || int(t.q_start.size()) != nb || int(t.v_start.size()) != nb ||
+        int(t.X_PF.size()) != 12 * nb || int(t.R_MB.size()) != 9 * nb || int(t.axis.size()) != 3 * nb ||
+        int(t.mass.size()) != nb || int(t.com.size()) != 3 * nb || int(t.inertia.size()) != 6 * nb ||
+        int(t.damping.size()) != t.nv || int(t.actuated.size()) != t.nv || int(t.gravity.size()) != 3 ||
+        int(t.geom_type.size()) != ng || int(t.geom_dims.size()) != 3 * ng || int(t.X_BG.size()) != 12 * ng ||
+        int(t.pair_geomB.size()) != np)
+      throw std::runtime_error("MultibodyPlant::FromTables: inconsistent table sizes");
+    auto pad = [](auto v) { if (v.empty()) v.resize(1); return v; };
+    p.parent_ = t.parent, p.jt_ = t.joint_type, p.qs_ = t.q_start, p.vs_ = t.v_start, p.act_ = pad(t.actuated);
+    p.gb_ = pad(t.geom_body), p.gt_ = pad(t.geom_type), p.pa_ = pad(t.pair_geomA), p.pb_ = pad(t.pair_geomB);
+    p.xpf_ = t.X_PF, p.rmb_ = t.R_MB, p.axis_ = t.axis, p.damp_ = pad(t.damping), p.mass_ = t.mass, p.com_ = t.com;
+    p.inertia_ = t.inertia, p.grav_ = t.gravity, p.gd_ = pad(t.geom_dims), p.xbg_ = pad(t.X_BG);
+    idto_model_desc& d = p.d_;
+    d.nbodies = nb, d.nq = t.nq, d.nv = t.nv, d.ngeoms = ng, d.npairs = np;
+    p.bind();
+    return p;
+  }
+  MultibodyPlant() = default;
+  MultibodyPlant(const MultibodyPlant& o) { *this = o; }
+  MultibodyPlant& operator=(const MultibodyPlant& o) {  // the descriptor points into this object's own vectors
+    d_ = o.d_, dt_ = o.dt_;
+    parent_ = o.parent_, jt_ = o.jt_, qs_ = o.qs_, vs_ = o.vs_, act_ = o.act_, gb_ = o.gb_, gt_ = o.gt_, pa_ = o.pa_, pb_ = o.pb_;
+    xpf_ = o.xpf_, rmb_ = o.rmb_, axis_ = o.axis_, damp_ = o.damp_, mass_ = o.mass_, com_ = o.com_;
+    inertia_ = o.inertia_, grav_ = o.grav_, gd_ = o.gd_, xbg_ = o.xbg_;
+    bind();
+    return *this;
+  }
   static MultibodyPlant LoadBaked(const std::string& path, double time_step) {
     std::ifstream f(path);
     if (!f) throw std::runtime_error("cannot open baked model " + path);
@@ -197,13 +236,7 @@ class MultibodyPlant {
     rd(p.xpf_, 12 * nb), rd(p.rmb_, 9 * nb), rd(p.axis_, 3 * nb), rd(p.damp_, d.nv), rd(p.mass_, nb);
     rd(p.com_, 3 * nb), rd(p.inertia_, 6 * nb), rd(p.grav_, 3), rd(p.gd_, 3 * ng), rd(p.xbg_, 12 * ng);
     if (!f) throw std::runtime_error("malformed baked model " + path);
-    d.parent = p.parent_.data(), d.joint_type = p.jt_.data(), d.q_start = p.qs_.data(), d.v_start = p.vs_.data();
-    d.actuated = p.act_.data(), d.geom_body = p.gb_.data(), d.geom_type = p.gt_.data();
-    d.pair_geomA = p.pa_.data(), d.pair_geomB = p.pb_.data();
-    d.X_PF = p.xpf_.data(), d.R_MB = p.rmb_.data(), d.axis = p.axis_.data(), d.damping = p.damp_.data();
-    d.mass = p.mass_.data(), d.com = p.com_.data(), d.inertia = p.inertia_.data();
-    d.geom_dims = p.gd_.data(), d.X_BG = p.xbg_.data();
-    for (int i = 0; i < 3; ++i) d.gravity[i] = p.grav_[i];
+    p.bind();
     return p;
   }
   double time_step() const { return dt_; }
@@ -212,6 +245,16 @@ class MultibodyPlant {
   const idto_model_desc& desc() const { return d_; }
 
  private:
+  void bind() {
+    idto_model_desc& d = d_;
+    d.parent = parent_.data(), d.joint_type = jt_.data(), d.q_start = qs_.data(), d.v_start = vs_.data();
+    d.actuated = act_.data(), d.geom_body = gb_.data(), d.geom_type = gt_.data();
+    d.pair_geomA = pa_.data(), d.pair_geomB = pb_.data();
+    d.X_PF = xpf_.data(), d.R_MB = rmb_.data(), d.axis = axis_.data(), d.damping = damp_.data();
+    d.mass = mass_.data(), d.com = com_.data(), d.inertia = inertia_.data();
+    d.geom_dims = gd_.data(), d.X_BG = xbg_.data();
+    for (int i = 0; i < 3; ++i) d.gravity[i] = grav_[i];
+  }
   idto_model_desc d_{};
   double dt_{0};
   std::vector<int> parent_, jt_, qs_, vs_, act_, gb_, gt_, pa_, pb_;
@@ -224,6 +267,29 @@ inline void ThrowOnError(int rc, const char* what) {
   if (rc != IDTO_OK) throw std::runtime_error(std::string(what) + ": " + idto_last_error());
 }
 
+// ---- optimizer/inverse_dynamics_partials.h:20-85, velocity_partials.h:19-39, penta_diagonal_matrix.h ------------
+struct InverseDynamicsPartials {
+  std::vector<MatrixXd> dtau_dqm, dtau_dqt, dtau_dqp;  // [num_steps] of nv x nq (dqm[0] = NaN, dqt[0] = dqm[1] = 0)
+};
+struct VelocityPartials {
+  std::vector<MatrixXd> dvt_dqt, dvt_dqm;  // [num_steps + 1] of nv x nq (dvt_dqm[0] = NaN)
+};
+struct PentaDiagonalMatrix {  // symmetric: D_i = B_{i+1}^T, E_i = A_{i+2}^T (penta_diagonal_matrix.cc:64-105)
+  std::vector<MatrixXd> A, B, C, D, E;
+  int block_rows() const { return int(C.size()); }
+  int block_size() const { return C.empty() ? 0 : C[0].rows(); }
+};
+// optimizer/trajectory_optimizer_state.h: q and everything computed from it.  Here: a view of the device-resident
+// cache of one WarmStart; the Eval* accessors of TrajectoryOptimizer compute what is stale and mirror it to the host.
+class TrajectoryOptimizerState {
+ public:
+  explicit TrajectoryOptimizerState(idto_solver_t s = nullptr) : s_(s) {}
+  idto_solver_t handle() const { return s_; }
+
+ private:
+  idto_solver_t s_;
+};
+
 // ---- optimizer/warm_start.h:23-76 ---------------------------------------------------------------------------
 class WarmStart {
  public:
@@ -231,6 +297,7 @@ class WarmStart {
             const std::vector<VectorXd>& q_guess)
       : T_(T), nq_(nq) {
     ThrowOnError(idto_solver_create(model, &pd, &p, 1, &s_), "idto_solver_create");
+    state = TrajectoryOptimizerState(s_);
     set_q(q_guess);
   }
   ~WarmStart() { if (s_) idto_solver_destroy(s_); }
@@ -269,6 +336,7 @@ class WarmStart {
   }
   idto_solver_t handle() const { return s_; }
   int version{0};
+  TrajectoryOptimizerState state;  // warm_start.h:63
 
  private:
   idto_solver_t s_{nullptr};
@@ -351,6 +419,44 @@ class TrajectoryOptimizer {
     return (why == 0 && iters == K) ? kMaxIterationsReached : kSuccess;  // cc:2648-2650
   }
 
+  // ---- evaluators (trajectory_optimizer.h:125-453): compute what is stale on the device, mirror to the host ------
+  std::vector<VectorXd> EvalV(const TrajectoryOptimizerState& st) const { return rows(st, 0, "v", num_steps() + 1, nv()); }
+  std::vector<VectorXd> EvalA(const TrajectoryOptimizerState& st) const { return rows(st, 0, "a", num_steps(), nv()); }
+  std::vector<VectorXd> EvalTau(const TrajectoryOptimizerState& st) const { return rows(st, 0, "tau", num_steps(), nv()); }
+  double EvalCost(const TrajectoryOptimizerState& st) const { return flat(st, 0, "cost")[0]; }
+  std::vector<MatrixXd> EvalNplus(const TrajectoryOptimizerState& st) const {
+    return blocks(flat(st, 0, "Nplus"), num_steps() + 1, nv(), nq());
+  }
+  InverseDynamicsPartials EvalInverseDynamicsPartials(const TrajectoryOptimizerState& st) const {
+    InverseDynamicsPartials p;
+    p.dtau_dqm = blocks(flat(st, 1, "dtau_dqm"), num_steps(), nv(), nq());
+    p.dtau_dqt = blocks(flat(st, 1, "dtau_dqt"), num_steps(), nv(), nq());
+    p.dtau_dqp = blocks(flat(st, 1, "dtau_dqp"), num_steps(), nv(), nq());
+    return p;
+  }
+  VelocityPartials EvalVelocityPartials(const TrajectoryOptimizerState& st) const {  // cc:962-973
+    VelocityPartials p;
+    p.dvt_dqt = blocks(flat(st, 0, "dvt_dqt"), num_steps() + 1, nv(), nq());
+    p.dvt_dqm = blocks(flat(st, 0, "dvt_dqm"), num_steps() + 1, nv(), nq());
+    return p;
+  }
+  VectorXd EvalGradient(const TrajectoryOptimizerState& st) const { return vec(flat(st, 2, "g")); }
+  VectorXd EvalScaledGradient(const TrajectoryOptimizerState& st) const { return vec(flat(st, 2, "gs")); }
+  VectorXd EvalScaleFactors(const TrajectoryOptimizerState& st) const { return vec(flat(st, 2, "D")); }
+  PentaDiagonalMatrix EvalHessian(const TrajectoryOptimizerState& st) const { return penta(st, "H_A", "H_B", "H_C"); }
+  PentaDiagonalMatrix EvalScaledHessian(const TrajectoryOptimizerState& st) const { return penta(st, "Hs_A", "Hs_B", "Hs_C"); }
+  VectorXd EvalEqualityConstraintViolations(const TrajectoryOptimizerState& st) const { return vec(flat(st, 0, "h")); }
+  MatrixXd EvalEqualityConstraintJacobian(const TrajectoryOptimizerState& st) const {  // dense (nu T) x n, cc:1292-1334
+    const std::vector<double> J = flat(st, 2, "J");
+    MatrixXd out(num_equality_constraints(), (num_steps() + 1) * nq());
+    for (int j = 0; j < out.cols(); ++j)
+      for (int i = 0; i < out.rows(); ++i) out(i, j) = J[size_t(j) * out.rows() + i];
+    return out;
+  }
+  VectorXd EvalLagrangeMultipliers(const TrajectoryOptimizerState& st) const { return vec(flat(st, 2, "lambda")); }
+  double EvalMeritFunction(const TrajectoryOptimizerState& st) const { return flat(st, 2, "merit")[0]; }
+  VectorXd EvalMeritFunctionGradient(const TrajectoryOptimizerState& st) const { return vec(flat(st, 2, "gm")); }
+
   void ResetInitialConditions(const VectorXd& q_init, const VectorXd& v_init) {  // h:463-468
     if (q_init.size() != plant_->num_positions() || v_init.size() != plant_->num_velocities())
       throw std::runtime_error("ResetInitialConditions: wrong sizes");
@@ -365,6 +471,53 @@ class TrajectoryOptimizer {
   }
 
  private:
+  int nq() const { return plant_->num_positions(); }
+  int nv() const { return plant_->num_velocities(); }
+  // stage: 0 trajectory-level entries, 1 + ID partials, 2 + gradient / Hessian / constraints / multipliers
+  std::vector<double> flat(const TrajectoryOptimizerState& st, int stage, const char* name) const {
+    idto_solver_t s = st.handle();
+    if (!s) throw std::runtime_error("Eval*: empty TrajectoryOptimizerState");
+    ThrowOnError(stage == 0 ? idto_eval_trajectory(s) : (stage == 1 ? idto_eval_derivatives(s) : idto_eval_assembly(s)),
+                 "idto_eval");
+    const long n = idto_field_size(s, name);
+    if (n < 0) throw std::runtime_error(std::string("unknown cache entry ") + name);
+    std::vector<double> buf(size_t(n > 0 ? n : 1));
+    ThrowOnError(idto_get(s, name, buf.data()), "idto_get");
+    buf.resize(size_t(n));
+    return buf;
+  }
+  static VectorXd vec(const std::vector<double>& x) {
+    VectorXd v(int(x.size()));
+    for (size_t i = 0; i < x.size(); ++i) v[int(i)] = x[i];
+    return v;
+  }
+  std::vector<VectorXd> rows(const TrajectoryOptimizerState& st, int stage, const char* name, int n, int w) const {
+    const std::vector<double> x = flat(st, stage, name);
+    std::vector<VectorXd> out(n, VectorXd(w));
+    for (int t = 0; t < n; ++t)
+      for (int i = 0; i < w; ++i) out[t][i] = x[size_t(t) * w + i];
+    return out;
+  }
+  static std::vector<MatrixXd> blocks(const std::vector<double>& x, int n, int r, int c) {  // column-major blocks
+    std::vector<MatrixXd> out(n, MatrixXd(r, c));
+    for (int t = 0; t < n; ++t)
+      for (int j = 0; j < c; ++j)
+        for (int i = 0; i < r; ++i) out[t](i, j) = x[(size_t(t) * c + j) * r + i];
+    return out;
+  }
+  PentaDiagonalMatrix penta(const TrajectoryOptimizerState& st, const char* a, const char* b, const char* c) const {
+    PentaDiagonalMatrix H;
+    const int nb = num_steps() + 1, k = nq();
+    H.A = blocks(flat(st, 2, a), nb, k, k), H.B = blocks(flat(st, 2, b), nb, k, k), H.C = blocks(flat(st, 2, c), nb, k, k);
+    H.D.assign(nb, MatrixXd(k, k)), H.E.assign(nb, MatrixXd(k, k));
+    for (int i = 0; i < nb; ++i)
+      for (int r = 0; r < k; ++r)
+        for (int cc = 0; cc < k; ++cc) {
+          if (i + 1 < nb) H.D[i](r, cc) = H.B[i + 1](cc, r);
+          if (i + 2 < nb) H.E[i](r, cc) = H.A[i + 2](cc, r);
+        }
+    return H;
+  }
   struct Flat {  // ProblemDefinition -> idto_problem_desc (column-major matrices, flattened trajectories)
     std::vector<double> q_init, v_init, q_nom, v_nom;
     idto_problem_desc desc{};
@@ -380,16 +533,20 @@ class TrajectoryOptimizer {
       desc.Qq = p.Qq.data(), desc.Qv = p.Qv.data(), desc.Qf_q = p.Qf_q.data(), desc.Qf_v = p.Qf_v.data(), desc.R = p.R.data();
     }
   };
-  idto_params c_params() const {
+  idto_params c_params() const { return ToC(params_); }
+
+ public:
+  using PublicFlat = Flat;
+  static idto_params ToC(const SolverParameters& s) {
     idto_params p;
     idto_params_default(&p);
-    const SolverParameters& s = params_;
     p.max_iterations = s.max_iterations, p.gradients_method = int(s.gradients_method);
     p.normalize_quaternions = s.normalize_quaternions, p.contact_stiffness = s.contact_stiffness;
     p.dissipation_velocity = s.dissipation_velocity, p.stiction_velocity = s.stiction_velocity;
     p.friction_coefficient = s.friction_coefficient, p.smoothing_factor = s.smoothing_factor;
     p.scaling = s.scaling, p.scaling_method = int(s.scaling_method), p.equality_constraints = s.equality_constraints;
     p.Delta0 = s.Delta0, p.Delta_max = s.Delta_max, p.check_convergence = s.check_convergence;
+    if (s.linear_solver == SolverParameters::kDenseLdlt) p.linear_solver = IDTO_LINSOLVE_DENSE_LDLT;  // cc:2088-2093
     const ConvergenceCriteriaTolerances& t = s.convergence_tolerances;
     p.tol_rel_cost_reduction = t.rel_cost_reduction, p.tol_abs_cost_reduction = t.abs_cost_reduction;
     p.tol_rel_gradient_along_dq = t.rel_gradient_along_dq, p.tol_abs_gradient_along_dq = t.abs_gradient_along_dq;
@@ -397,6 +554,7 @@ class TrajectoryOptimizer {
     return p;
   }
 
+ private:
   const Diagram<T>* diagram_{nullptr};
   const MultibodyPlant* plant_{nullptr};
   ProblemDefinition prob_;
@@ -404,6 +562,107 @@ class TrajectoryOptimizer {
   idto_model_t model_{nullptr};
   std::vector<int> unactuated_dofs_;
   int version_{0};
+};
+
+// ---- batch of independent solves over several GPUs, in one process ------------------------------
+// The reference's threading contract: independent optimizers / WarmStarts may run on different threads
+// (trajectory_optimizer.h:1096 shared context).  Here: one model + one batched solver per device, one
+// host thread per device for every call, contiguous batch slices, no collective — the in-process twin of
+// `torchrun bench.py --gpus N`.  Host arrays are indexed by GLOBAL problem.
+class MultiGpuBatch {
+ public:
+  MultiGpuBatch(const MultibodyPlant& plant, const ProblemDefinition& prob, const SolverParameters& params, int batch,
+                int num_devices = 0)
+      : nq_(plant.num_positions()), nv_(plant.num_velocities()), T_(prob.num_steps), B_(batch) {
+    int ndev = idto_device_count();
+    if (ndev == 0) throw std::runtime_error("MultiGpuBatch: no CUDA device (there is no CPU fallback)");
+    if (num_devices > 0 && num_devices < ndev) ndev = num_devices;
+    if (ndev > batch) ndev = batch;
+    TrajectoryOptimizer<double> proto_check(nullptr, &plant, prob, params);  // size checks, like a single optimizer
+    shards_.resize(ndev);
+    run([&](int d) {
+      Shard& sh = shards_[d];
+      sh.b0 = int(size_t(batch) * d / ndev), sh.b1 = int(size_t(batch) * (d + 1) / ndev);
+      ThrowOnError(idto_set_device(d), "idto_set_device");
+      ThrowOnError(idto_model_create(&plant.desc(), &sh.model), "idto_model_create");
+      typename TrajectoryOptimizer<double>::PublicFlat f(prob, plant);
+      const idto_params p = TrajectoryOptimizer<double>::ToC(params);
+      ThrowOnError(idto_solver_create(sh.model, &f.desc, &p, sh.b1 - sh.b0, &sh.solver), "idto_solver_create");
+    });
+  }
+  ~MultiGpuBatch() {
+    for (Shard& sh : shards_) {
+      if (sh.solver) idto_solver_destroy(sh.solver);
+      if (sh.model) idto_model_destroy(sh.model);
+    }
+  }
+  MultiGpuBatch(const MultiGpuBatch&) = delete;
+  int num_devices() const { return int(shards_.size()); }
+  int batch() const { return B_; }
+  // q: [batch][(T+1) nq]
+  void set_q(const std::vector<double>& q) {
+    const size_t w = size_t(T_ + 1) * nq_;
+    if (q.size() != w * B_) throw std::runtime_error("MultiGpuBatch::set_q: wrong size");
+    run([&](int d) { ThrowOnError(idto_set_q(shards_[d].solver, q.data() + w * shards_[d].b0), "idto_set_q"); });
+  }
+  void ResetInitialConditions(const std::vector<double>& q_init, const std::vector<double>& v_init) {
+    if (q_init.size() != size_t(B_) * nq_ || v_init.size() != size_t(B_) * nv_)
+      throw std::runtime_error("MultiGpuBatch::ResetInitialConditions: wrong sizes");
+    run([&](int d) {
+      const Shard& sh = shards_[d];
+      ThrowOnError(idto_reset_initial_conditions(sh.solver, q_init.data() + size_t(sh.b0) * nq_,
+                                                 v_init.data() + size_t(sh.b0) * nv_), "idto_reset_initial_conditions");
+    });
+  }
+  // SolveFromWarmStart for every problem: iterations run per problem; stats [batch][max_iterations][IDTO_NUM_STATS]
+  std::vector<int> Solve(int max_iterations, std::vector<double>* stats = nullptr) {
+    std::vector<int> iters(B_, 0);
+    const size_t w = size_t(max_iterations > 0 ? max_iterations : 1) * IDTO_NUM_STATS;
+    if (stats) stats->assign(w * B_, 0.0);
+    run([&](int d) {
+      const Shard& sh = shards_[d];
+      ThrowOnError(idto_solve(sh.solver, max_iterations, iters.data() + sh.b0, nullptr,
+                              stats ? stats->data() + w * sh.b0 : nullptr), "idto_solve");
+    });
+    return iters;
+  }
+  // field of every problem, concatenated in global order (names: idto_get)
+  std::vector<double> Get(const char* name) {
+    const long n = idto_field_size(shards_[0].solver, name);
+    if (n < 0) throw std::runtime_error(std::string("unknown cache entry ") + name);
+    std::vector<double> out(size_t(n) * B_);
+    run([&](int d) {
+      const Shard& sh = shards_[d];
+      ThrowOnError(idto_eval_trajectory(sh.solver), "idto_eval_trajectory");
+      ThrowOnError(idto_get(sh.solver, name, out.data() + size_t(n) * sh.b0), "idto_get");
+    });
+    return out;
+  }
+
+ private:
+  struct Shard {
+    idto_model_t model{nullptr};
+    idto_solver_t solver{nullptr};
+    int b0{0}, b1{0};
+  };
+  template <class F>
+  void run(F f) {  // one host thread per device; exceptions are re-thrown on the caller's thread
+    std::vector<std::thread> th;
+    std::vector<std::string> err(shards_.size());
+    for (int d = 0; d < int(shards_.size()); ++d)
+      th.emplace_back([&, d] {
+        try {
+          f(d);
+        } catch (const std::exception& e) {
+          err[d] = e.what()[0] ? e.what() : "error";
+        }
+      });
+    for (auto& t : th) t.join();
+    for (const std::string& e : err)
+      if (!e.empty()) throw std::runtime_error(e);
+  }
+  std::vector<Shard> shards_;
+  int nq_, nv_, T_, B_;
 };
 
 }  // namespace optimizer

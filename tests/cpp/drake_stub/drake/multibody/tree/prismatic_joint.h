@@ -1,0 +1,3 @@
+// stand-in for <drake/multibody/tree/prismatic_joint.h>: see ../stub_impl.h
+#pragma once
+#include "drake/stub_impl.h"

@@ -97,6 +97,69 @@ int main(int argc, char** argv) {
   CHECK(after[0][0] == 0.32 && after[0][2] == 0.02);
   for (int t = 1; t <= 40; ++t)
     for (int i = 0; i < 3; ++i) CHECK(std::fabs(after[t][i] - before[t][i]) < 1e-12);
+
+  // Eval* accessors on the warm start's state (trajectory_optimizer.h:125-453)
+  {
+    const TrajectoryOptimizerState& st = ws->state;
+    const std::vector<VectorXd> v = opt1.EvalV(st), tau = opt1.EvalTau(st);
+    CHECK(v.size() == 41 && tau.size() == 40 && v[0].size() == 3);
+    const VelocityPartials vp = opt1.EvalVelocityPartials(st);  // cc:962-973: N+ = I for 1-dof joints
+    CHECK(vp.dvt_dqt.size() == 41 && std::fabs(vp.dvt_dqt[3](1, 1) - 1.0 / time_step) < 1e-12);
+    CHECK(std::isnan(vp.dvt_dqm[0](0, 0)) && std::fabs(vp.dvt_dqm[3](2, 2) + 1.0 / time_step) < 1e-12);
+    CHECK(vp.dvt_dqt[3](0, 1) == 0.0);
+    const InverseDynamicsPartials idp = opt1.EvalInverseDynamicsPartials(st);
+    CHECK(idp.dtau_dqp.size() == 40 && idp.dtau_dqp[0].rows() == 3 && std::isnan(idp.dtau_dqm[0](0, 0)));
+    const PentaDiagonalMatrix H = opt1.EvalHessian(st);
+    CHECK(H.block_rows() == 41 && H.block_size() == 3 && H.C[0](0, 0) == 1.0 && H.C[0](1, 0) == 0.0);  // C_0 = I
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) CHECK(H.D[4](r, c) == H.B[5](c, r) && H.E[4](r, c) == H.A[6](c, r));
+    const VectorXd g = opt1.EvalGradient(st), lam = opt1.EvalLagrangeMultipliers(st);
+    CHECK(g.size() == 41 * 3 && g[0] == 0.0 && lam.size() == 40);
+    const MatrixXd J = opt1.EvalEqualityConstraintJacobian(st);
+    CHECK(J.rows() == 40 && J.cols() == 123);
+    CHECK(std::fabs(opt1.EvalMeritFunction(st) - (opt1.EvalCost(st) + [&] {
+            const VectorXd h = opt1.EvalEqualityConstraintViolations(st);
+            double s = 0;
+            for (int i = 0; i < 40; ++i) s += h[i] * lam[i];
+            return s;
+          }())) < 1e-9 * std::fmax(1.0, std::fabs(opt1.EvalCost(st))));
+  }
+
+  // kDenseLdlt (cc:2088-2093) through the C++ API: same iterates as the penta-diagonal solver
+  {
+    SolverParameters pd = params;
+    pd.max_iterations = 5, pd.linear_solver = SolverParameters::kDenseLdlt;
+    TrajectoryOptimizer<double> optd(diagram, &plant, problem, pd);
+    TrajectoryOptimizerSolution<double> sd;
+    TrajectoryOptimizerStats<double> std_;
+    optd.Solve(q_guess, &sd, &std_);
+    for (int k = 0; k < 5; ++k)
+      CHECK(std::fabs(std_.iteration_costs[k] - stats.iteration_costs[k]) < 1e-6 * std::fabs(stats.iteration_costs[k]));
+  }
+
+  // a batch over every GPU of the process (one host thread per device, no collective): each problem equals the
+  // single solve above
+  {
+    SolverParameters pb = params;
+    pb.max_iterations = 4;
+    const int B = 5;
+    MultiGpuBatch mb(plant, problem, pb, B);
+    std::vector<double> q0(size_t(B) * 41 * 3);
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t <= 40; ++t)
+        for (int i = 0; i < 3; ++i) q0[(size_t(b) * 41 + t) * 3 + i] = q_guess[t][i];
+    mb.set_q(q0);
+    std::vector<double> st;
+    const std::vector<int> it = mb.Solve(4, &st);
+    CHECK(mb.num_devices() >= 1 && int(it.size()) == B);
+    for (int b = 0; b < B; ++b) {
+      CHECK(it[b] == 4);
+      for (int k = 0; k < 4; ++k)
+        CHECK(std::fabs(st[(size_t(b) * 4 + k) * IDTO_NUM_STATS] - stats.iteration_costs[k]) < 1e-9 * stats.iteration_costs[k]);
+    }
+    CHECK(mb.Get("q").size() == size_t(B) * 41 * 3);
+    std::printf("MultiGpuBatch: %d problems on %d device(s)\n", B, mb.num_devices());
+  }
   std::printf("C++ API test OK\n");
   return 0;
 }

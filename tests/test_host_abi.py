@@ -129,3 +129,14 @@ def test_baked_model_json_roundtrip(tmp_path):
     m2 = BakedModel.load(p)
     for k in BakedModel._INT + BakedModel._DBL:
         assert np.array_equal(np.asarray(getattr(m, k)), np.asarray(getattr(m2, k))), k
+
+
+def test_top_level_pyidto_module_reexports_the_binding():
+    """python_bindings/pyidto.cc:12-23: the examples do `from pyidto import TrajectoryOptimizer, ...`."""
+    import pyidto
+    from idto_b200 import pyidto as impl
+    for name in ("TrajectoryOptimizer", "ProblemDefinition", "SolverParameters", "TrajectoryOptimizerSolution",
+                 "TrajectoryOptimizerStats", "FindIdtoResource"):
+        assert getattr(pyidto, name) is getattr(impl, name)
+    p = pyidto.SolverParameters()
+    assert p.max_iterations == 100 and p.Delta0 == 1e-1  # python_bindings/test/solver_parameters_test.py

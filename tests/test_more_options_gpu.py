@@ -1,0 +1,100 @@
+"""GPU-vs-oracle parity of the options SURVEY.md §8(f4) lists after the headline path: the sphere-cylinder closed
+form on the device, and the reference's kDenseLdlt debugging solver (cc:2088-2093)."""
+import copy
+
+import numpy as np
+import pytest
+
+from idto_b200 import problems
+from idto_b200.bake import GEOM_CAPSULE, GEOM_CYLINDER
+from idto_b200.types import GRAD_CENTRAL, GRAD_FORWARD, LINSOLVE_DENSE_LDLT, LINSOLVE_TWISTED
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(x, y, s=None):
+    return float(np.nanmax(np.abs(np.asarray(x) - np.asarray(y))) / (s or max(1.0, np.nanmax(np.abs(y)))))
+
+
+@pytest.mark.parametrize("method", [GRAD_FORWARD, GRAD_CENTRAL])
+def test_sphere_cylinder_contact_matches_oracle(oracle_mod, method):
+    """The spinner_capsule model with its capsule re-registered as a Cylinder of the same radius and length (Drake's
+    DistanceToPoint<Cylinder>: flat caps, barrel, rims): eleven finger spheres against it, GPU vs oracle."""
+    from idto_b200 import capi
+    m, dt, prob, params, guess = problems.spinner_capsule(gradients_method=method)
+    m = copy.deepcopy(m)
+    m.geom_type = np.where(m.geom_type == GEOM_CAPSULE, GEOM_CYLINDER, m.geom_type).astype(m.geom_type.dtype)
+    assert (m.geom_type == GEOM_CYLINDER).sum() == 1
+    gs = capi.BatchSolver(capi.Model(m), dt, prob, params, 2)
+    oc = oracle_mod.Oracle(m, dt, prob, params)
+    rng = np.random.default_rng(1)
+    q = np.array(guess, float)
+    q[1:] += rng.normal(0, 0.05, q[1:].shape).cumsum(axis=0) * 0.3
+    gs.set_q(q)
+    oc.set_q(q)
+    gs.eval(1)
+    oc.eval(1)
+    v, a = oc.get("v").reshape(-1, m.nv), oc.get("a").reshape(-1, m.nv)
+    active = np.array([oc.inverse_dynamics(q[t + 1], v[t + 1], a[t])[1] for t in range(prob.num_steps)])
+    assert active.any() and not active.all()
+    assert _rel(gs.get("tau")[0], oc.get("tau")) < 1e-11
+    sc = max(1.0, np.nanmax(np.abs(oc.get("dtau_dqp"))))
+    for f in ("dtau_dqm", "dtau_dqt", "dtau_dqp"):
+        assert _rel(gs.get(f)[1], oc.get(f), sc) < 2e-6, f
+    gs.set_q(guess)
+    oc.set_q(guess)
+    it, _, stats = gs.solve(12)
+    k, _, so = oc.solve(12)
+    assert np.array_equal(stats[0, :, 1], so[:, 1]) and _rel(stats[0, :, 0], so[:, 0]) < 1e-6
+
+
+@pytest.mark.parametrize("name,kw", [("spinner", {}), ("hopper", {"T": 20}), ("mini_cheetah", {"T": 12}), ("acrobot", {})])
+def test_dense_ldlt_solver_cross_checks_the_penta_diagonal_one(oracle_mod, name, kw):
+    """linear_solver = dense_ldlt re-solves H~ x = -gm without using the block structure; the Gauss-Newton step,
+    the dogleg point and a few iterations agree with the penta-diagonal sweep (and so with the oracle)."""
+    from idto_b200 import capi
+    out = {}
+    for ls in (LINSOLVE_TWISTED, LINSOLVE_DENSE_LDLT):
+        m, dt, prob, params, guess = getattr(problems, name)(gradients_method=GRAD_CENTRAL, **kw)
+        params.linear_solver = ls
+        gs = capi.BatchSolver(capi.Model(m), dt, prob, params, 2)
+        rng = np.random.default_rng(7)
+        q = np.array(guess, float)
+        q[1:] += rng.normal(0, 0.03, q[1:].shape)
+        gs.set_q(np.stack([np.array(guess, float), q]))
+        gs.eval(3)
+        res = {f: gs.get(f)[1].copy() for f in ("dqH", "dq", "lambda", "gm")}
+        gs.set_q(np.array(guess, float))
+        it, _, stats = gs.solve(3)
+        res["stats"], res["q"] = stats[0].copy(), gs.solution()[0][0].copy()
+        out[ls] = res
+    a, b = out[LINSOLVE_TWISTED], out[LINSOLVE_DENSE_LDLT]
+    assert np.array_equal(a["lambda"], b["lambda"]) and np.array_equal(a["gm"], b["gm"])  # same sweep before it
+    assert not np.array_equal(a["dqH"], b["dqH"])  # a different factorisation really ran
+    # two backward-stable solvers: cond(H~) eps apart (cond ~ 1e10 on the acrobot, 2e11 on the quadruped)
+    assert _rel(b["dqH"], a["dqH"]) < 1e-4 and _rel(b["dq"], a["dq"]) < 1e-4
+    assert np.array_equal(a["stats"][:, 1], b["stats"][:, 1])  # same accept / reject decisions
+    assert _rel(b["stats"][:, 0], a["stats"][:, 0]) < 1e-6 and _rel(b["q"], a["q"]) < 1e-5
+
+
+def test_multi_device_batch_solver_equals_single_device(oracle_mod):
+    """One process, every visible GPU (one host thread + solver per device, contiguous slices, no collective):
+    problem b of the sharded batch equals problem b of a single-device batch, bit for bit."""
+    from idto_b200 import capi
+    m, dt, prob, params, guess = problems.hopper(T=20, gradients_method=GRAD_CENTRAL)
+    B = 7
+    q0, v0, qg = problems.perturbed_batch(m, prob, B)
+    md = capi.MultiDeviceBatchSolver(m, dt, prob, params, B)
+    md.reset_initial_conditions(q0, v0)
+    md.set_q(qg)
+    it, _, stats = md.solve(3)
+    q, v, tau = md.solution()
+    one = capi.BatchSolver(capi.Model(m), dt, prob, params, B)
+    one.reset_initial_conditions(q0, v0)
+    one.set_q(qg)
+    it1, _, stats1 = one.solve(3)
+    q1, v1, tau1 = one.solution()
+    assert len(md.shards) == min(capi.device_count(), B) and sum(s.B for s in md.shards) == B
+    assert np.array_equal(it, it1) and np.array_equal(stats, stats1)
+    assert np.array_equal(q, q1) and np.array_equal(tau, tau1)
+    assert md.get("cost").shape == (B, 1)
