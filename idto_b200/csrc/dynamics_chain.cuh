@@ -72,8 +72,18 @@ struct BodyState {
   M3 R;
   V3 p, w, v, al, ac;
 };
-__device__ __forceinline__ double shfl_d(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
-__device__ __forceinline__ V3 shfl_v(V3 a, int src) { return {shfl_d(a.x, src), shfl_d(a.y, src), shfl_d(a.z, src)}; }
+__device__ __forceinline__ double shfl_d(unsigned wm, double x, int src) { return __shfl_sync(wm, x, src); }
+__device__ __forceinline__ V3 shfl_v(unsigned wm, V3 a, int src) {
+  return {shfl_d(wm, a.x, src), shfl_d(wm, a.y, src), shfl_d(wm, a.z, src)};
+}
+// lanes of the CG-lane group that contains the calling lane: every warp-level primitive of chain_eval is scoped to
+// it, so a group can run (or skip) an evaluation on its own — no lane ever executes an evaluation only to keep a
+// neighbour's shuffles alive (those redundant evaluations wrote shared poses twice: racecheck hazards)
+template <int CG>
+__device__ __forceinline__ unsigned group_mask() {
+  if (CG == 32) return 0xffffffffu;
+  return ((1u << (CG & 31)) - 1u) << ((threadIdx.x & 31) / CG * CG);
+}
 
 // Geometry of candidate pair ip at the pose in `Po` (cc:272-320): signed distance, contact normal (from A into B,
 // negated: the direction of the force on B), contact point (midpoint of the witness points).
@@ -143,7 +153,7 @@ struct Perturb {
 
 enum { kEvalFull = 0, kEvalSharedPose = 1, kEvalSharedPoseNoBias = 2, kEvalPoseOnly = 3 };
 
-// How one evaluation visits the contact pairs (all fields group-uniform; near_in == nullptr must be warp-uniform).
+// How one evaluation visits the contact pairs (all fields group-uniform).
 struct PairWalk {
   const int* near_in = nullptr;  // pruned models: walk this near list instead of every candidate
   int* near_out = nullptr;       // pruned models: write the near list of this (unperturbed) pose
@@ -153,7 +163,7 @@ struct PairWalk {
                                  // force this evaluation computes (the caller zero-fills it); may differ per group
 };
 
-// One inverse-dynamics evaluation by a group of CG lanes (all 32 lanes of the warp must call).
+// One inverse-dynamics evaluation by a group of CG lanes (all CG lanes of the group must call, converged).
 //   MODE kEvalFull:           pose from q (written to `Po`), velocities, forces -> tau
 //   MODE kEvalSharedPose:     pose read from `Po` (computed earlier), velocities, forces -> tau
 //   MODE kEvalSharedPoseNoBias: tau = M(q) a only (no gravity / damping / contact / velocity terms)
@@ -176,6 +186,7 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
   const SModel& M = C.M;
   const int nb = M.nb;
   const int gbase = (threadIdx.x & 31) / CG * CG;
+  const unsigned wm = group_mask<CG>();
   constexpr bool kPose = MODE == kEvalFull || MODE == kEvalPoseOnly;
   constexpr bool kStorePose = MODE == kEvalPoseOnly;  // body poses are kept only when they will be shared
   constexpr bool kDyn = MODE != kEvalPoseOnly;
@@ -189,14 +200,14 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
   for (int l = 0; l < NLEV; ++l) {
     const int b = (l < C.nlev && c < CG) ? C.levbody[l * CG + c] : -1;
     BodyState par = prev;
-    if (l < C.nlev && C.levcross[l]) {  // warp-uniform: some body of this level hangs off another chain
+    if (l < C.nlev && C.levcross[l]) {  // group-uniform: some body of this level hangs off another chain
       const int src = (b >= 0 && C.plane[b] >= 0 && C.plane[b] != c) ? gbase + C.plane[b] : (threadIdx.x & 31);
 #pragma unroll
-      for (int e = 0; e < 9; ++e) par.R.m[e] = shfl_d(prev.R.m[e], src);
-      par.p = shfl_v(prev.p, src);
+      for (int e = 0; e < 9; ++e) par.R.m[e] = shfl_d(wm, prev.R.m[e], src);
+      par.p = shfl_v(wm, prev.p, src);
       if (kDyn) {
-        par.w = shfl_v(prev.w, src), par.v = shfl_v(prev.v, src);
-        par.al = shfl_v(prev.al, src), par.ac = shfl_v(prev.ac, src);
+        par.w = shfl_v(wm, prev.w, src), par.v = shfl_v(wm, prev.v, src);
+        par.al = shfl_v(wm, prev.al, src), par.ac = shfl_v(wm, prev.ac, src);
       }
     }
     if (b >= 0) {
@@ -343,7 +354,7 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
       }
     }
   }
-  __syncwarp();
+  __syncwarp(wm);
 
   // ---- contact pairs: geometry (cc:272-320, 349-359) and forces (cc:322-373), one pair per lane ---------
   // Pair slots: slot == candidate index when every candidate has one (C.prune == 0); otherwise the active pairs
@@ -357,7 +368,7 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
         // candidates of this evaluation: the near list of the unperturbed pose, or all of them
         const bool walk_near = pw.near_in != nullptr;
         const int ncand = pw.skip ? 0 : (walk_near ? min(max(pw.near_in[0], 0), kMaxActivePairs) : M.np);
-        const int nmax = __reduce_max_sync(0xffffffffu, ncand);  // the ballots need a warp-uniform trip count
+        const int nmax = ncand;  // group-uniform (near_in and skip are)
         const unsigned gmask = CG == 32 ? 0xffffffffu : ((1u << (CG & 31)) - 1u), below = (1u << c) - 1u;
         int count = 0, ncount = 0;
         for (int k0 = 0; k0 < nmax; k0 += CG) {
@@ -371,8 +382,8 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
             act = pg.distance <= sc.threshold;
             nearby = pg.distance <= sc.threshold + pw.margin;
           }
-          const unsigned grp = (__ballot_sync(0xffffffffu, act) >> gbase) & gmask;
-          const unsigned ngrp = (__ballot_sync(0xffffffffu, nearby) >> gbase) & gmask;
+          const unsigned grp = (__ballot_sync(wm, act) >> gbase) & gmask;
+          const unsigned ngrp = (__ballot_sync(wm, nearby) >> gbase) & gmask;
           const int pos = count + __popc(grp & below), npos = ncount + __popc(ngrp & below);
           if (act && pos < pst) {
             store_V(Po.PG, pst, pos, pg.nhat);
@@ -388,7 +399,7 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
           if (pw.near_out) pw.near_out[0] = ncount < kMaxActivePairs ? ncount : kMaxActivePairs;
           if (count > pst || (pw.near_out && ncount > kMaxActivePairs)) atomicExch(sc.status, IDTO_ERR_CONTACT_OVERFLOW);
         }
-        __syncwarp();
+        __syncwarp(wm);
         if (pw.act_out) {  // what the force pass will walk: the compacted list, read back from shared memory
           const int cnt = min(int(ids[pst]), pst);
           for (int is = c; is < cnt; is += CG) pw.act_out[slot_pair(ids, is, M.np)] = 1;
@@ -440,7 +451,7 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
         store_V(S.PF, pst, is, f_BC);
       }
     }
-    __syncwarp();
+    __syncwarp(wm);
   }
   if (!kDyn) return;
 
@@ -496,7 +507,7 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
         }
       }
     }
-    __syncwarp();
+    __syncwarp(wm);
   }
 }
 

@@ -144,33 +144,35 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   pt.owner = owner, pt.local = local, pt.sl = sl, pt.quatcol = quatcol;
   __syncthreads();  // zrow
 
-  // ---- phase 0: shared poses of q_{t+1} (even groups) and q_{t+2} (odd groups), first warp(s) of a slot ----
+  // ---- phase 0: shared poses of the slot: q_{t+1} by its group 0, q_{t+2} by its group 1 ------------------------
+  // (every warp-level primitive of chain_eval is scoped to the calling group, so exactly one group writes each
+  // shared pose; the other groups wait at the barrier below.  Earlier builds let every lane of the warps holding
+  // groups 0 and 1 run these evaluations and store the same values redundantly: racecheck hazards.)
+  const unsigned gm = group_mask<CG>();
   {
-    // the warp(s) holding groups 0 and 1 of a slot; all their lanes run the evaluation (shuffles, ballots), the
-    // lanes of other groups redundantly for the pose their own parity selects.  One call site: the warp must
-    // stay converged inside chain_eval.
-    const bool mine = valid_slot && ii < 2;
-    if (__any_sync(0xffffffffu, mine)) {
+    const int ncol_here = min(ncol, dm.nfull - chunk * ncol);  // columns this CTA really has (last chunk: fewer)
+    const bool slot_live = valid_slot && (force || bf.ctl[b].derivs_dirty);
+    if (slot_live && ii < 2 && ii < ncol_here) {
       Perturb none = pt;
       none.owner = -1;
-      const bool second = (ii & 1) != 0 && ncol != 1;
-      const PoseSmem P0 = second ? PC : PB;
+      const bool second = ii == 1;
       // the pose of q_{t+2} only serves the bias-free evaluations of phase C: no contact geometry
       PairWalk pw;
       pw.near_in = near_list ? near_list + size_t(tp1 - 1) * kNearStride : nullptr;
       pw.skip = second;
-      chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, P0, S, c, qB + size_t(second ? tp2 : tp1) * nq, vB, aB, none, T0,
-                                          nullptr, pw);
-      pw.skip = true;
-      if (ncol == 1)
+      chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, second ? PC : PB, S, c, qB + size_t(second ? tp2 : tp1) * nq, vB, aB,
+                                          none, T0, nullptr, pw);
+      if (ncol_here == 1) {  // a single column: its group computes both poses
+        pw.skip = true;
         chain_eval<CG, NLEV, kEvalPoseOnly>(C, sc, PC, S, c, qB + size_t(tp2) * nq, vB, aB, none, T0, nullptr, pw);
+      }
     }
   }
 
   constexpr int NK = METHOD == IDTO_GRAD_CENTRAL4 ? 4 : (METHOD == IDTO_GRAD_CENTRAL ? 2 : 1);
   // combine the stencil points of one column: rows r = c, c+CG, ... of column i
   auto emit = [&](double* __restrict__ dst_block, const double* __restrict__ tau_base, bool ok) {
-    __syncwarp();
+    __syncwarp(gm);
     if (ok && live)
       for (int r = c; r < nv; r += CG) {
         double val;
@@ -182,21 +184,23 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
           val = 2.0 / 3.0 * T2[r] / dq - 1.0 / 12.0 * (T0[r] - T1[r]) / dq;  // cc:782-783 (T2 = tau+ - tau-)
         dst_block[size_t(i) * nv + r] = val;
       }
-    __syncwarp();
+    __syncwarp(gm);
   };
   auto stash_d1 = [&]() {  // CD4: keep tau(+dq) - tau(-dq) while T0/T1 are reused for +-2dq
-    __syncwarp();
+    __syncwarp(gm);
     for (int r = c; r < nv; r += CG) T2[r] = T0[r] - T1[r];
-    __syncwarp();
+    __syncwarp(gm);
   };
 
   // ---- A: tau[t-1] = ID(q_t^e, v_t^e, a_{t-1}^e)   (cc:526-531, 763-787) --------------------------------
+  // (groups without a live column — padding lanes of the last warp, slots beyond the batch, problems whose
+  // derivatives are current — skip the evaluations: nothing they would compute is kept)
   PairWalk pwA;  // the perturbed pose can only activate pairs of the near list of q_t
   pwA.near_in = near_list ? near_list + size_t(t - 1) * kNearStride : nullptr;
 #pragma unroll 1
-  for (int kk = 0; kk < NK; ++kk) {
+  for (int kk = 0; kk < (live ? NK : 0); ++kk) {
     const double m = ((kk & 1) ? -1.0 : 1.0) * ((kk >= 2) ? 2.0 : 1.0);
-    if (bf.act_fd && live) pwA.act_out = bf.act_fd + ((((size_t(b) * T + (t - 1)) * nq + i) * 4 + kk) * dm.np);
+    if (bf.act_fd) pwA.act_out = bf.act_fd + ((((size_t(b) * T + (t - 1)) * nq + i) * 4 + kk) * dm.np);
     pt.dq = m * dq, pt.cv = m * dv, pt.ca = m * da, pt.uv = 1.0, pt.ua = 1.0, pt.nv3 = nt3, pt.na3 = nt3;
     chain_eval<CG, NLEV, kEvalFull>(C, sc, PA, S, c, qB + size_t(t) * nq, vB + size_t(t) * nv,
                                     aB + size_t(t - 1) * nv, pt, (kk & 1) ? T1 : T0, nullptr, pwA);
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   emit(bf.dqp + (size_t(b) * T + (t - 1)) * nv * nq, bf.st.tau + (size_t(b) * T + (t - 1)) * nv, true);
 
   __syncthreads();  // shared poses complete
+  if (!live) return;  // (no block-wide barrier below)
 
   // ---- B: tau[t] = ID(q_{t+1}, v_{t+1}^e, a_t^e)   (cc:533-540, 788-814) ---------------------------------
   const int tb = t < T ? t : T - 1;  // a row index that exists even when the result is discarded
@@ -222,8 +227,8 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   // ---- C: dtau_dqm[t+1] = M(q_{t+2}) N+_{t+1} / dt^2   (cc:552-561) ---------------------------------------
   pt.dq = 0.0, pt.cv = 0.0, pt.ca = 1.0, pt.uv = 1.0, pt.ua = 1.0, pt.nv3 = ntp3, pt.na3 = ntp3;
   chain_eval<CG, NLEV, kEvalSharedPoseNoBias>(C, sc, PC, S, c, qB + size_t(tp2) * nq, zrow, zrow, pt, T0);
-  __syncwarp();
-  if (t < T - 1 && live) {
+  __syncwarp(gm);
+  if (t < T - 1) {
     double* dst = bf.dqm + (size_t(b) * T + (t + 1)) * nv * nq + size_t(i) * nv;
     for (int r = c; r < nv; r += CG) dst[r] = 1 / sc.dt / sc.dt * T0[r];
   }
@@ -259,14 +264,12 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
   Perturb none;
   none.owner = -1, none.local = 0, none.sl = 0, none.quatcol = false;
   none.dq = none.cv = none.ca = 0.0, none.uv = none.ua = 1.0, none.nv3 = none.na3 = {0, 0, 0};
-  // (groups that are not live evaluate item (0, 0) and write its records: same values as its owner writes, or,
-  // if problem 0 is not stale, as are there already)
-  double* rec = STASH ? stash + size_t(ctl[live ? b : 0].stash_sel ^ scratch) * stash_half +
-                            (size_t(live ? b : 0) * T + (live ? t : 0)) * dm.nb * kStashDoubles
+  if (!live) return;  // (chain_eval's warp-level primitives are scoped to the group: idle groups simply leave)
+  double* rec = STASH ? stash + size_t(ctl[b].stash_sel ^ scratch) * stash_half + (size_t(b) * T + t) * dm.nb * kStashDoubles
                       : nullptr;
-  const double* qrow = tb.q + (size_t(live ? b : 0) * (T + 1) + (live ? t : 0) + 1) * nq;
+  const double* qrow = tb.q + (size_t(b) * (T + 1) + t + 1) * nq;
   PairWalk pw;
-  if (dm.prune && tb.near && live) {
+  if (dm.prune && tb.near) {
     // what a finite-difference perturbation of one coordinate (|dq| <= 2 sqrt(eps) max(1,|q_i|), cc:506, 763) can
     // move a geometry centre by: |dq| times a lever arm bounded by the chain lengths plus the joint travel
     double qmax = 1.0;
@@ -274,15 +277,12 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
     pw.near_out = tb.near + (size_t(b) * T + t) * kNearStride;
     pw.margin = 4e-7 * qmax * (dm.reach + dm.nb * qmax);
   }
-  if (act_base && live) pw.act_out = act_base + (size_t(b) * T + t) * dm.np;
-  chain_eval<CG, NLEV, kEvalFull, STASH>(C, sc, PA, S, c, qrow,
-                                         tb.v + (size_t(live ? b : 0) * (T + 1) + (live ? t : 0) + 1) * nv,
-                                         tb.a + (size_t(live ? b : 0) * T + (live ? t : 0)) * nv, none, T0, rec, pw);
-  __syncwarp();
-  if (live) {
-    double* tau = tb.tau + (size_t(b) * T + t) * nv;
-    for (int r = c; r < nv; r += CG) tau[r] = T0[r];
-  }
+  if (act_base) pw.act_out = act_base + (size_t(b) * T + t) * dm.np;
+  chain_eval<CG, NLEV, kEvalFull, STASH>(C, sc, PA, S, c, qrow, tb.v + (size_t(b) * (T + 1) + t + 1) * nv,
+                                         tb.a + (size_t(b) * T + t) * nv, none, T0, rec, pw);
+  __syncwarp(group_mask<CG>());
+  double* tau = tb.tau + (size_t(b) * T + t) * nv;
+  for (int r = c; r < nv; r += CG) tau[r] = T0[r];
 }
 
 // ---- dispatch on (chain group size, padded tree depth) ------------------------------------------------------

@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r2g_tests.log
+timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r2g_bench.json 2> gpurun_out/r2g_bench.err
+timeout 900 compute-sanitizer --tool racecheck --print-limit 30 python tools/sanitize_small.py > gpurun_out/r2g_racecheck.log 2>&1
+tail -5 gpurun_out/r2g_racecheck.log
