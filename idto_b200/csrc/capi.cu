@@ -185,7 +185,7 @@ void make_view(const idto_solver_s* s, int b0, int nb, SolverConsts* scv, Solver
   for (TrajBuf* tb : {&v.st, &v.sc}) {
     tb->q += o * T1 * nq, tb->v += o * T1 * nv, tb->a += o * T * nv, tb->tau += o * T * nv;
     tb->Nplus += o * T1 * nv * nq, tb->cost += o, tb->h += o * nh;
-    if (tb->near) tb->near += o * T * kNearStride;
+    if (tb->near) tb->near += o * T * near_stride(s->model->dm.nact);
   }
   v.q_init += o * nq, v.v_init += o * nv, v.q_nom += o * T1 * nq, v.v_nom += o * T1 * nv;
   v.dqm += o * T * nv * nq, v.dqt += o * T * nv * nq, v.dqp += o * T * nv * nq;
@@ -338,8 +338,9 @@ int check_status(idto_solver_s* s) {
   const int st = *s->status_host;
   if (st != 0) {
     if (st == IDTO_ERR_CONTACT_OVERFLOW)
-      set_last_error("more than " + std::to_string(kMaxActivePairs) +
-                     " contact pairs within the activation distance in one inverse-dynamics evaluation");
+      set_last_error("more than " + std::to_string(s->model->dm.nact) +
+                     " contact pairs within the activation distance in one inverse-dynamics evaluation (raise "
+                     "IDTO_MAX_ACTIVE_PAIRS before creating the model)");
     else if (st == IDTO_ERR_UNSUPPORTED)
       set_last_error("no KKT sweep kernel for this block size");
     else
@@ -440,7 +441,7 @@ int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
   DevModel& dm = m->dm;
   dm.nb = nb, dm.nbp = nbp, dm.nq = d->nq, dm.nv = d->nv, dm.ng = ngp, dm.np = np, dm.npp = npp;
   dm.prune = np > kMaxActivePairs ? 1 : 0;
-  dm.nact = dm.prune ? kMaxActivePairs : npp;
+  dm.nact = npp;  // (pruned models: set below, once the column split is known)
   {
     double chain = 0.0, off = 0.0;
     for (int k = 0; k < nb; ++k) {
@@ -589,6 +590,12 @@ int idto_model_create(const idto_model_desc* d, idto_model_t* out) {
   while (dt.size() % 2) dt.push_back(0.0);
   dm.itab_bytes = int(it.size() * sizeof(int));
   dm.dtab_bytes = int(dt.size() * sizeof(double));
+  if (dm.prune) {  // capacity of the per-evaluation active list (and of the near lists): even, at most npp
+    if (const char* e = std::getenv("IDTO_MAX_ACTIVE_PAIRS"))
+      dm.nact = std::min(npp, (std::max(8, std::atoi(e)) + 1) / 2 * 2);
+    else
+      dm.nact = chain_fit_pair_slots(dm, d->nv);
+  }
   int* di = nullptr;
   double* dd = nullptr;
   if (m->mem.get(&di, it.size()) != cudaSuccess || m->mem.get(&dd, dt.size()) != cudaSuccess ||
@@ -703,7 +710,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
     alloc(&tb->q, nTq), alloc(&tb->v, nTv), alloc(&tb->a, nA), alloc(&tb->tau, nA), alloc(&tb->Nplus, nN);
     alloc(&tb->cost, B), alloc(&tb->h, size_t(B) * nh);
     tb->near = nullptr;
-    if (m->dm.prune) ok = ok && A.get(&tb->near, size_t(B) * T * kNearStride) == cudaSuccess;
+    if (m->dm.prune) ok = ok && A.get(&tb->near, size_t(B) * T * near_stride(m->dm.nact)) == cudaSuccess;
   }
   alloc(&s->q_init, size_t(B) * nq), alloc(&s->v_init, size_t(B) * nv), alloc(&s->q_nom, nTq), alloc(&s->v_nom, nTv);
   alloc(&bf.dqm, nP), alloc(&bf.dqt, nP), alloc(&bf.dqp, nP);

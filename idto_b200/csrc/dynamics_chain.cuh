@@ -367,7 +367,7 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
       if (C.prune) {
         // candidates of this evaluation: the near list of the unperturbed pose, or all of them
         const bool walk_near = pw.near_in != nullptr;
-        const int ncand = pw.skip ? 0 : (walk_near ? min(max(pw.near_in[0], 0), kMaxActivePairs) : M.np);
+        const int ncand = pw.skip ? 0 : (walk_near ? min(max(pw.near_in[0], 0), pst) : M.np);
         const int nmax = ncand;  // group-uniform (near_in and skip are)
         const unsigned gmask = CG == 32 ? 0xffffffffu : ((1u << (CG & 31)) - 1u), below = (1u << c) - 1u;
         int count = 0, ncount = 0;
@@ -391,13 +391,13 @@ __device__ __forceinline__ void chain_eval(const CModel& C, const SolverConsts& 
             Po.PG[6 * pst + pos] = contact_fn_c(sc, pg.distance);
             ids[pos] = double(ip);
           }
-          if (nearby && pw.near_out && npos < kMaxActivePairs) pw.near_out[1 + npos] = ip;
+          if (nearby && pw.near_out && npos < pst) pw.near_out[1 + npos] = ip;
           count += __popc(grp), ncount += __popc(ngrp);
         }
         if (c == 0) {
           ids[pst] = double(count < pst ? count : pst);
-          if (pw.near_out) pw.near_out[0] = ncount < kMaxActivePairs ? ncount : kMaxActivePairs;
-          if (count > pst || (pw.near_out && ncount > kMaxActivePairs)) atomicExch(sc.status, IDTO_ERR_CONTACT_OVERFLOW);
+          if (pw.near_out) pw.near_out[0] = ncount < pst ? ncount : pst;
+          if (count > pst || (pw.near_out && ncount > pst)) atomicExch(sc.status, IDTO_ERR_CONTACT_OVERFLOW);
         }
         __syncwarp(wm);
         if (pw.act_out) {  // what the force pass will walk: the compacted list, read back from shared memory

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   const double* aB = bf.st.a + size_t(b) * T * nv;
   const int tp1 = t < T ? t + 1 : t, tp2 = t < T - 1 ? t + 2 : t;  // clamped rows for predicated-off work
   // pruned models: near lists of the unperturbed poses of this problem, entry j for q_{j+1} (k_tau_chain)
+  const int kNearStride = near_stride(dm.nact);
   const int* near_list = dm.prune ? bf.st.near + size_t(b) * T * kNearStride : nullptr;
 
   // ---- column bookkeeping (every lane computes it: no shuffles needed) ------------------------------------
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
     // move a geometry centre by: |dq| times a lever arm bounded by the chain lengths plus the joint travel
     double qmax = 1.0;
     for (int e = 0; e < nq; ++e) qmax = fmax(qmax, fabs(qrow[e]));
-    pw.near_out = tb.near + (size_t(b) * T + t) * kNearStride;
+    pw.near_out = tb.near + (size_t(b) * T + t) * near_stride(dm.nact);
     pw.margin = 4e-7 * qmax * (dm.reach + dm.nb * qmax);
   }
   if (act_base) pw.act_out = act_base + (size_t(b) * T + t) * dm.np;
@@ -352,13 +353,27 @@ static int chain_key(const DevModel& dm) {
   }
 
 // Shared memory one CTA of the ID kernels needs for this model (a single slot is the minimum).  The contact-pair
-// scratch is sized by dm.nact: every candidate pair for small models, kMaxActivePairs compacted slots for models
+// scratch is sized by dm.nact: every candidate pair for small models, the compacted-list capacity for models
 // with more candidates than that (allegro hand: 188).
 int chain_min_smem_bytes(const DevModel& dm, int nv, int method) {
   const int ntau = method == IDTO_GRAD_CENTRAL4 ? 3 : 2;
   const int partials = chain_smem_bytes(dm, nv, ntau, 1, 1);  // one slot, one column per CTA
   const int tau = model_smem_bytes(dm) + (64 / dm.cgroup) * cgroup_doubles(dm, nv, 1) * 8;
   return partials > tau ? partials : tau;
+}
+
+// Capacity of the per-evaluation active-pair list for a model with more than kMaxActivePairs candidates: the
+// largest even count up to kDefaultPairSlots for which ALL full columns of a (b,t) slot still share one CTA (a
+// larger list splits the columns over several CTAs, each with few warps and its own copy of the shared poses: the
+// allegro hand's ID partials ran 2x slower with 64 slots than with 32); if not even kMaxActivePairs slots fit that
+// way the columns are split anyway and the list gets kDefaultPairSlots.
+int chain_fit_pair_slots(DevModel dm, int nv) {
+  const int hi = std::min(dm.npp, kDefaultPairSlots);
+  for (int n = hi; n >= kMaxActivePairs; n -= 2) {
+    dm.nact = n;
+    if (chain_smem_bytes(dm, nv, 2, 1, std::max(dm.nfull, 1)) <= 226 * 1024) return n;
+  }
+  return hi;
 }
 
 bool chain_supported(const DevModel& dm) {

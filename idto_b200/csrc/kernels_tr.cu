@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
 // (cc:2601-2611, 2653-2689) and the Delta update (cc:2613-2622).  `commit`=0 only evaluates rho.
 // One CTA per (problem, block row) computes its rows of H~ s, s = D^-1 dq, and the partial sums of
 // s.H~s, gm.s, h(q+dq).lambda and |h|^2; the last CTA of a problem owns the scalar logic and the commit.
-__global__ void __launch_bounds__(kRowThreads) k_trust_update(SolverConsts sc, SolverBufs bf, int commit) {
+__global__ void __launch_bounds__(kRowThreads) k_trust_update(SolverConsts sc, SolverBufs bf, int commit, int kNearStride) {
   __shared__ double xs[5 * 32], terms[5 * 32];
   __shared__ double red[32];
   __shared__ int s_accept;
@@ -416,13 +416,13 @@ void launch_dogleg(const SolverConsts& sc, const SolverBufs& bf, cudaStream_t st
 
 void launch_trust_update(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool commit,
                          cudaStream_t stream) {
-  (void)dm;
   g_launch_counter += 1;
   static bool attr_set[kMaxDevices] = {};
   if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_trust_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   }
-  k_trust_update<<<sc.B*(sc.T + 1), kRowThreads, 5 * sc.nq * sc.nq * 8, stream>>>(sc, bf, commit ? 1 : 0);
+  k_trust_update<<<sc.B*(sc.T + 1), kRowThreads, 5 * sc.nq * sc.nq * 8, stream>>>(sc, bf, commit ? 1 : 0,
+                                                                                near_stride(dm.nact));
 }
 
 }  // namespace idto

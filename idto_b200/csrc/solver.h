@@ -26,12 +26,13 @@ constexpr int kMaxLevels = 8;    // tree depth supported by the chain-lane kerne
 // Contact pairs one inverse-dynamics evaluation can have ACTIVE (signed distance <= threshold, cc:268-275) at the
 // same time when the model has more candidate pairs than this: each evaluation then compacts the active pairs,
 // in candidate order, into a list of this capacity (dynamics_chain.cuh) instead of keeping every candidate.
-constexpr int kMaxActivePairs = 32;
+constexpr int kMaxActivePairs = 32;   // models with more candidate pairs than this compact their active pairs
+constexpr int kDefaultPairSlots = 64; // ... into DevModel::nact slots per evaluation (IDTO_MAX_ACTIVE_PAIRS overrides)
 // Near list of a pose (pruned models): [0] count, [1..] candidate indices, ascending, of the pairs whose signed
 // distance at the UNPERTURBED pose is within the activation distance plus a margin that bounds what a finite-
 // difference perturbation can move (k_tau_chain writes it while it walks every candidate anyway; the perturbed
 // evaluations of the ID partials walk it instead of the candidates).
-constexpr int kNearStride = kMaxActivePairs + 1;
+__host__ __device__ inline int near_stride(int nact) { return nact + 1; }
 
 // Baked model on the device: two SoA tables (ints, doubles) copied to shared memory by TMA.
 struct DevModel {
@@ -39,7 +40,8 @@ struct DevModel {
   const double* dtab;
   int itab_bytes, dtab_bytes;  // multiples of 16
   int nb, nbp, nq, nv, ng, np, npp, nlevels, group;  // nbp/npp: padded strides; group: lanes per evaluation
-  int nact, prune;  // per-evaluation pair slots (npp, or kMaxActivePairs when np is larger: prune = 1)
+  int nact, prune;  // per-evaluation pair slots: npp, or (np > kMaxActivePairs: prune = 1) the capacity of the
+                    // compacted active list (kDefaultPairSlots unless IDTO_MAX_ACTIVE_PAIRS says otherwise)
   double reach;     // bound on the lever arm of any joint on any geometry centre at q = 0 (near-list margin)
   // chain decomposition (lane = kinematic chain, step = tree level): cgroup lanes per evaluation
   int cgroup, nchains, ngb, ngd;  // ngb: bodies carrying geometry, ngd: geometries on moving bodies
@@ -76,7 +78,7 @@ struct SolverConsts {
 // One TrajectoryOptimizerState's trajectory-level cache (state.h:37-351) for the batch.
 struct TrajBuf {
   double *q, *v, *a, *tau, *Nplus, *cost, *h;
-  int* near;  // [B][T][kNearStride] near list of pose q_{t+1} (pruned models only, else null)
+  int* near;  // [B][T][near_stride(nact)] near list of pose q_{t+1} (pruned models only, else null)
 };
 
 // Per-problem trust-region control block (device resident; host never reads it mid-solve).
@@ -149,6 +151,7 @@ int launch_mpc_advance(const SolverConsts& sc, const SolverBufs& b, const double
                        cudaStream_t stream);
 int partials_smem_bytes(const DevModel& dm, int nq);
 bool chain_supported(const DevModel& dm);
+int chain_fit_pair_slots(DevModel dm, int nv);  // default capacity of the active-pair list of a pruned model
 int chain_min_smem_bytes(const DevModel& dm, int nv, int method);  // one-slot CTA of the chain-lane ID kernels
 void launch_partials_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
                            cudaStream_t stream);

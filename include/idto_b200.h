@@ -31,7 +31,8 @@ enum {
   IDTO_ERR_CUDA = -3,          /* CUDA runtime error; see idto_last_error() */
   IDTO_ERR_FACTORIZATION = -4, /* penta-diagonal / dense factorisation failed */
   IDTO_ERR_NO_DEVICE = -5,     /* no CUDA device: there is NO CPU fallback */
-  IDTO_ERR_CONTACT_OVERFLOW = -6 /* more contact pairs active at once than an evaluation can hold (32) */
+  IDTO_ERR_CONTACT_OVERFLOW = -6 /* more contact pairs active at once than an evaluation's list holds (models with
+                                  * > 32 candidate pairs: 64 slots, or IDTO_MAX_ACTIVE_PAIRS at model creation) */
 };
 
 /* ------------------------------------------------------- baked model tables

@@ -1,7 +1,8 @@
 """Allegro hand (BASELINE config 'allegro_hand in-hand sphere rotation, 22 DOF, many contacts'): the SDF bake
 the oracle side and the CUDA path.  188 CANDIDATE pairs do not fit the per-evaluation shared-memory scratch of the
 inverse-dynamics kernels, so for this model every evaluation compacts its ACTIVE pairs (distance <= threshold, the
-pairs the reference visits, cc:272-275) into a 32-slot list; more than that at once is an error, not a silent drop."""
+pairs the reference visits, cc:272-275) into a list of 64 slots (IDTO_MAX_ACTIVE_PAIRS raises it up to the number
+of candidates); more than that at once is an error, not a silent drop."""
 import numpy as np
 import pytest
 
@@ -106,7 +107,7 @@ def test_allegro_cache_entries_match_oracle(oracle_mod, method):
     oc.eval(4)
     v, a = oc.get("v").reshape(-1, m.nv), oc.get("a").reshape(-1, m.nv)
     nact = [int(np.sum(oc.inverse_dynamics(q[t + 1], v[t + 1], a[t])[1])) for t in range(prob.num_steps)]
-    assert 4 <= min(nact) and max(nact) <= 32, nact  # contact is really exercised, and fits the pair slots
+    assert 4 <= min(nact) and max(nact) <= 64, nact  # contact is really exercised, and fits the pair slots
     for f in ("Nplus", "v", "a", "tau", "cost", "h"):
         assert _relerr(gs.get(f)[0], oc.get(f)) < 1e-11, f
     sc = max(1.0, np.abs(oc.get("dtau_dqp")).max())
@@ -169,3 +170,27 @@ def test_allegro_too_many_simultaneous_contacts_is_an_error():
     gs.set_q(np.array(guess))
     with pytest.raises(capi.IdtoError, match="contact pairs within the activation distance"):
         gs.eval(1)
+
+
+@pytest.mark.gpu
+def test_allegro_pair_capacity_follows_the_environment(oracle_mod, monkeypatch):
+    """The same over-active configuration with IDTO_MAX_ACTIVE_PAIRS = number of candidates: every pair fits, the
+    CTA shape adapts (one column per CTA), and tau / the partials agree with the oracle, which has no limit —
+    like the reference (cc:272-386)."""
+    from idto_b200 import capi
+    m, dt, prob, params, guess = problems.allegro_hand(T=4, gradients_method=GRAD_FORWARD)
+    params.smoothing_factor = 0.05
+    monkeypatch.setenv("IDTO_MAX_ACTIVE_PAIRS", str(m.npairs))
+    gs = capi.BatchSolver(capi.Model(m), dt, prob, params, 1)
+    oc = oracle_mod.Oracle(m, dt, prob, params)
+    q = np.array(guess)
+    gs.set_q(q)
+    oc.set_q(q)
+    gs.eval(1)
+    oc.eval(1)
+    v, a = oc.get("v").reshape(-1, m.nv), oc.get("a").reshape(-1, m.nv)
+    assert int(oc.inverse_dynamics(q[1], v[1], a[0])[1].sum()) > 64
+    assert _relerr(gs.get("tau")[0], oc.get("tau")) < 1e-11
+    sc = max(1.0, np.abs(oc.get("dtau_dqp")).max())
+    for f in ("dtau_dqm", "dtau_dqt", "dtau_dqp"):
+        assert _relerr(gs.get(f)[0], oc.get(f), sc) < 2e-6, f
