@@ -144,7 +144,7 @@ void enqueue_derivatives(idto_solver_s* s, bool force) {
   }
   launch_partials(s->model->dm, s->sc, s->bf, force, s->stream);
 }
-void enqueue_assembly(idto_solver_s* s, bool force) {
+void enqueue_assembly(idto_solver_s* s, bool force, bool with_gm = true) {
   {
     Prof p(s, "assemble");
     launch_assemble(s->model->dm, s->sc, s->bf, force, s->stream);
@@ -155,22 +155,34 @@ void enqueue_assembly(idto_solver_s* s, bool force) {
   }
   {
     Prof p(s, "lagrange");
-    launch_lagrange(s->model->dm, s->sc, s->bf, force, s->stream);
+    launch_lagrange(s->model->dm, s->sc, s->bf, force, s->stream, with_gm);
   }
 }
+// Dogleg point and the model terms of the trust ratio; then the scalar tail of the iteration.
+void enqueue_dogleg(const SolverConsts& sc, const SolverBufs& bf, cudaStream_t st, bool gm_done) {
+  (void)gm_done;
+  launch_dogleg(sc, bf, st);
+}
+void enqueue_trust(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool commit, cudaStream_t st) {
+  if (trust_final_enabled())
+    launch_trust_final(dm, sc, bf, commit, st);
+  else
+    launch_trust_update(dm, sc, bf, commit, st);
+}
 void enqueue_iteration(idto_solver_s* s) {
+  const bool split = true;
   enqueue_trajectory(s, false, false);
   enqueue_derivatives(s, false);
-  enqueue_assembly(s, false);
+  enqueue_assembly(s, false, split);
   if (s->sc.check_convergence) launch_conv_check(s->sc, s->bf, s->stream);
   {
     Prof p(s, "dogleg");
-    launch_dogleg(s->sc, s->bf, s->stream);
+    enqueue_dogleg(s->sc, s->bf, s->stream, split);
   }
   enqueue_trajectory(s, true, true);
   {
     Prof p(s, "trust_update");
-    launch_trust_update(s->model->dm, s->sc, s->bf, true, s->stream);
+    enqueue_trust(s->model->dm, s->sc, s->bf, true, s->stream);
   }
 }
 
@@ -259,13 +271,14 @@ void enqueue_iterations_parts(idto_solver_s* s, const std::vector<Part>& P, int 
     }
     for (const Part& p : P) launch_partials(dm, p.sc, p.bf, false, p.st);
     for (const Part& p : P) launch_assemble(dm, p.sc, p.bf, false, p.st);
-    for (const Part& p : P) launch_lagrange(dm, p.sc, p.bf, false, p.st);
+    const bool split = true;
+    for (const Part& p : P) launch_lagrange(dm, p.sc, p.bf, false, p.st, split);
     for (const Part& p : P) {
       if (s->sc.check_convergence) launch_conv_check(p.sc, p.bf, p.st);
-      launch_dogleg(p.sc, p.bf, p.st);
+      enqueue_dogleg(p.sc, p.bf, p.st, split);
       launch_traj(dm, p.sc, p.bf, true, true, p.st);
       launch_tau(dm, p.sc, p.bf, true, true, p.st);
-      launch_trust_update(dm, p.sc, p.bf, true, p.st);
+      enqueue_trust(dm, p.sc, p.bf, true, p.st);
     }
   }
 }
@@ -911,7 +924,7 @@ int idto_eval_dogleg(idto_solver_t s) {
   cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   if (int rc = idto_eval_assembly(s)) return rc;
   k_set_ctl<<<(s->sc.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->sc.B, 2, 0.0);
-  launch_dogleg(s->sc, s->bf, s->stream);
+  enqueue_dogleg(s->sc, s->bf, s->stream, true);
   return check_status(s);
 }
 int idto_eval_trust_ratio(idto_solver_t s) {
@@ -919,7 +932,7 @@ int idto_eval_trust_ratio(idto_solver_t s) {
   cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   if (int rc = idto_eval_dogleg(s)) return rc;
   enqueue_trajectory(s, true, true);
-  launch_trust_update(s->model->dm, s->sc, s->bf, false, s->stream);
+  enqueue_trust(s->model->dm, s->sc, s->bf, false, s->stream);
   return check_status(s);
 }
 

@@ -734,7 +734,7 @@ void launch_factor(const SolverConsts& sc, const SolverBufs& bf, bool force, cud
 }
 
 void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, bool with_gm) {
   (void)dm;
   const int kb = sc.nq + (sc.eq ? sc.nu : 0);
   g_launch_counter += 1;
@@ -746,8 +746,10 @@ void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBuf
   else
     launched = launch_kkt_dispatch<1>(kb, sc, bf, force, stream);
   if (!launched) k_kkt_unsupported<<<1, 1, 0, stream>>>(bf.status);
+  const bool dense = sc.linear_solver == IDTO_LINSOLVE_DENSE_LDLT && bf.S;
+  (void)with_gm;
   launch_gm_matvec(sc, bf, force, stream);  // gm, merit, gHg, g.g
-  if (sc.linear_solver == IDTO_LINSOLVE_DENSE_LDLT && bf.S) {
+  if (dense) {
     static bool attr_set[kMaxDevices] = {};
     if (first_use_on_device(attr_set))
       cudaFuncSetAttribute(k_dense_ldlt, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);

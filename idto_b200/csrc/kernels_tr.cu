@@ -160,15 +160,17 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
   double* dqH = bf.dqH + size_t(b) * n;
   double* dqs = bf.tmp1 + size_t(b) * n;
   // pU = -(g.g / gHg) g / Delta  (cc:2157)
-  double pU2 = 0.0, pH2 = 0.0, a = 0.0, bq = 0.0;
+  double pU2 = 0.0, pH2 = 0.0, a = 0.0, bq = 0.0, xg = 0.0;
 #pragma unroll 4
   for (int e = tid; e < n; e += nt) {
     const double pu = -(gg / gHg) * gm[e] / Delta, ph = pH[e] / Delta;
     pU2 += pu * pu, pH2 += ph * ph;
     const double d = ph - pu;
     a += d * d, bq += pu * d;
+    xg += ph * gm[e];
   }
   pU2 = block_sum(pU2, red), pH2 = block_sum(pH2, red), a = block_sum(a, red), bq = block_sum(bq, red);
+  xg = block_sum(xg, red);  // gm . pH
   const double pUn = sqrt(pU2), pHn = sqrt(pH2);
   int active;
   double s = 0.0;
@@ -224,6 +226,21 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
     ctl->dq_norm = sqrt(dq2), ctl->dqH_norm = sqrt(dqH2), ctl->q_norm = sqrt(q2);
     ctl->dL_dq = gdq / bf.st.cost[b];
     ctl->gnorm = sqrt(gg);
+    // Model terms of the trust ratio for s = D^-1 dq = Delta y (cc:2008-2017): y is a combination of pU and pH, and
+    //   pU^T H~ pU = pU^T H~ pH = g.g^2 / (gHg Delta^2)   (pU = -(g.g / gHg) gm / Delta; H~ pH = -gm / Delta),
+    //   pH^T H~ pH = -(gm . pH) / Delta,
+    // H~ pH = -gm / Delta being what the KKT sweep solved (residual 1e-9 relative: tests/test_gpu_parity.py).
+    const double cuu = gg * gg / (gHg * Delta * Delta), chh = -xg / Delta;
+    double yHy;
+    if (branch == 0) {
+      yHy = cuu / pU2;
+    } else if (branch == 1) {
+      yHy = chh;
+    } else {
+      const double w = 1.0 - s;
+      yHy = w * w * cuu + 2.0 * s * w * cuu + s * s * chh;
+    }
+    ctl->ht = Delta * Delta * yHy, ctl->gt = gdq;  // gm . s, summed above like the reference does (cc:2518-2523)
   }
 }
 

@@ -84,6 +84,7 @@ struct TrajBuf {
 // Per-problem trust-region control block (device resident; host never reads it mid-solve).
 struct ProbCtl {
   double Delta, rho, prev_cost, merit, cost_kp, gnorm, hnorm, dq_norm, dqH_norm, q_norm, dL_dq;
+  double ht, gt;      // s.H~s and gm.s of the current dogleg step (k_dogleg_post), for k_trust_final (cc:2008-2017)
   double Delta_prev;  // Delta before the last update: restored when that step turns out to have converged (cc:2601-2622)
   int traj_dirty;    // q changed: v, a, tau, cost, h stale
   int derivs_dirty;  // partials / g / H / D / factor / lambda stale
@@ -132,8 +133,13 @@ void launch_partials(const DevModel& dm, const SolverConsts& sc, const SolverBuf
 void launch_assemble(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
                      cudaStream_t stream);
 void launch_factor(const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
+// KKT sweep (lambda, x = -H~^-1 gm) and, with_gm, the merit gradient / merit / Cauchy scalars that follow it
 void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool force,
-                     cudaStream_t stream);
+                     cudaStream_t stream, bool with_gm = true);
+// kernels_post.cu: scalar tail of the iteration (the model terms of the trust ratio come from k_dogleg_post)
+bool trust_final_enabled();
+void launch_trust_final(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b, bool commit,
+                        cudaStream_t stream);
 // register-resident two-sided KKT sweep (kernels_kkt2.cu); false if this block size is not instantiated
 bool launch_kkt_tw2(int kb, const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
 // third generation (kernels_kkt3.cu): single-warp LU + column-per-thread triangular solves; same contract

@@ -98,3 +98,29 @@ def test_multi_device_batch_solver_equals_single_device(oracle_mod):
     assert np.array_equal(it, it1) and np.array_equal(stats, stats1)
     assert np.array_equal(q, q1) and np.array_equal(tau, tau1)
     assert md.get("cost").shape == (B, 1)
+
+
+def test_trust_ratio_model_terms_match_the_explicit_matvec(monkeypatch):
+    """k_dogleg_post forms s.H~s from dot products (H~ pH = -gm / Delta is what the KKT sweep solved); k_trust_update
+    (IDTO_TRUST_MATVEC=1) multiplies H~ s out like the reference (cc:2008-2017).  Same rho, same decisions."""
+    from idto_b200 import capi
+    out = {}
+    for tag, env in (("dots", None), ("matvec", "1")):
+        if env:
+            monkeypatch.setenv("IDTO_TRUST_MATVEC", env)
+        res = []
+        for name, kw in (("mini_cheetah", {"T": 20}), ("hopper", {}), ("spinner", {})):
+            m, dt, prob, params, guess = getattr(problems, name)(gradients_method=GRAD_CENTRAL, **kw)
+            B = 3
+            q0, v0, qg = problems.perturbed_batch(m, prob, B)
+            gs = capi.BatchSolver(capi.Model(m), dt, prob, params, B)
+            gs.reset_initial_conditions(q0, v0)
+            gs.set_q(qg)
+            it, _, stats = gs.solve(6)
+            res.append(stats.copy())
+        out[tag] = res
+    assert capi.lib() is not None
+    for a, b in zip(out["dots"], out["matvec"]):
+        assert np.array_equal(a[:, :, 1], b[:, :, 1])                 # trust-region radii: same decisions
+        assert np.max(np.abs(a[:, :, 5] - b[:, :, 5])) < 1e-6 * max(1.0, np.max(np.abs(b[:, :, 5])))  # rho
+        assert _rel(a[:, :, 0], b[:, :, 0]) < 1e-9
