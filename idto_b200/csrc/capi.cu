@@ -758,6 +758,14 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   bf.q_init = s->q_init, bf.v_init = s->v_init, bf.q_nom = s->q_nom, bf.v_nom = s->v_nom;
   bf.stats = nullptr, bf.stats_cap = 0;
   bf.act_base = bf.act_fd = nullptr;
+  {
+    std::vector<double> cp(T + 1, 0.0);
+    if (T >= 2) cp[2] = 0.25;
+    for (int j = 3; j <= T - 2; ++j) cp[j] = 1.0 / (4.0 - cp[j - 1]);
+    double* dcp = nullptr;
+    if (A.get(&dcp, cp.size()) == cudaSuccess) cudaMemcpy(dcp, cp.data(), cp.size() * sizeof(double), cudaMemcpyHostToDevice);
+    bf.spline_cp = dcp;
+  }
   sc.Qq = dQq, sc.Qv = dQv, sc.Qfq = dQfq, sc.Qfv = dQfv, sc.R = dR, sc.unact = dun, sc.quat_starts = dqs;
   sc.status = bf.status;
   auto up_diag = [&](double* dst, const double* Mx, int n) {

@@ -8,7 +8,9 @@
 //     q_nom_t += selector o (q0 - q_nom_0)   (mpc_controller.cc:62-69);
 //   * ResetInitialConditions(q0, v0) (mpc_controller.cc:72) and every cache entry goes stale.
 // One thread per (problem, coordinate); the spline's tridiagonal system (uniform knots) is solved by the
-// Thomas recurrence in local memory.
+// Thomas recurrence in local memory.  fp64 divisions cost ~400 cycles each on this part: the kernel spent 30 us in
+// ~200 of them per thread; the reciprocals of h, h^2 and 6 are formed once, and the modified super-diagonal of the
+// recurrence (which depends on the horizon only) comes from a table made at solver creation.
 #include "solver.h"
 
 namespace idto {
@@ -23,7 +25,7 @@ __global__ void __launch_bounds__(64) k_mpc_advance(SolverConsts sc, SolverBufs 
                                                     double* q_nom) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = sc.nq, nv = sc.nv, N = sc.T;  // knots 0..N
-  const bool live = idx < sc.B * nq;  // (no early return: the CTA shares the spline coefficients below)
+  const bool live = idx < sc.B * nq;
   const int b = live ? idx / nq : 0, i = live ? idx % nq : 0;
   const double h = sc.dt;
   double* q = bf.st.q + size_t(b) * (N + 1) * nq + i;
@@ -32,22 +34,18 @@ __global__ void __launch_bounds__(64) k_mpc_advance(SolverConsts sc, SolverBufs 
   // second derivatives M_j of the not-a-knot spline on uniform knots:
   //   M_{j-1} + 4 M_j + M_{j+1} = 6 (y_{j+1} - 2 y_j + y_{j-1}) / h^2,  j = 1..N-1
   //   M_0 = 2 M_1 - M_2,  M_N = 2 M_{N-1} - M_{N-2}   =>   6 M_1 = rhs_1,  6 M_{N-1} = rhs_{N-1}
-  auto rhs = [&](int j) { return 6.0 * ((y[j + 1] - 2.0 * y[j]) + y[j - 1]) / (h * h); };
+  const double inv_h = 1.0 / h, six_inv_h2 = 6.0 / (h * h), sixth = 1.0 / 6.0;
+  auto rhs = [&](int j) { return ((y[j + 1] - 2.0 * y[j]) + y[j - 1]) * six_inv_h2; };
   if (N >= 4) {
-    M[1] = rhs(1) / 6.0;
-    M[N - 1] = rhs(N - 1) / 6.0;
+    M[1] = rhs(1) * sixth;
+    M[N - 1] = rhs(N - 1) * sixth;
     // Thomas on j = 2..N-2 with the known neighbours M_1, M_{N-1} moved to the right-hand side
     // (cp: modified super-diagonal, M doubles as the modified right-hand side)
     auto d = [&](int j) { return rhs(j) - (j == 2 ? M[1] : 0.0) - (j == N - 2 ? M[N - 1] : 0.0); };
     const double mN1 = M[N - 1];
-    // the modified super-diagonal cp[j] = 1 / (4 - cp[j-1]) depends on j only: one chain of N dependent
-    // divisions (fp64 division: ~400 cycles) per CTA instead of per thread
-    __shared__ double cp[kMaxKnots];
-    if (threadIdx.x == 0) {
-      cp[2] = 0.25;
-      for (int j = 3; j <= N - 2; ++j) cp[j] = 1.0 / (4.0 - cp[j - 1]);
-    }
-    __syncthreads();
+    // the modified super-diagonal cp[j] = 1 / (4 - cp[j-1]) depends on the horizon only: tabulated on the host at
+    // solver creation (a chain of N dependent fp64 divisions otherwise)
+    const double* __restrict__ cp = bf.spline_cp;
     M[2] = d(2) * 0.25;
     for (int j = 3; j <= N - 2; ++j) M[j] = (d(j) - M[j - 1]) * cp[j];
     M[N - 1] = mN1;
@@ -57,23 +55,23 @@ __global__ void __launch_bounds__(64) k_mpc_advance(SolverConsts sc, SolverBufs 
   } else if (N == 3) {  // four points: the not-a-knot spline is the cubic through them
     // M linear over the whole range: M_0 = 2 M_1 - M_2, M_3 = 2 M_2 - M_1, and the two interior equations
     //   6 M_1 = rhs_1 ... with M_2 unknown too: (2M_1 - M_2) + 4 M_1 + M_2 = 6 M_1;  M_1 + 4 M_2 + (2 M_2 - M_1) = 6 M_2
-    M[1] = rhs(1) / 6.0, M[2] = rhs(2) / 6.0;
+    M[1] = rhs(1) * sixth, M[2] = rhs(2) * sixth;
     M[0] = 2.0 * M[1] - M[2], M[3] = 2.0 * M[2] - M[1];
   } else if (N == 2) {  // three points: parabola
-    M[0] = M[1] = M[2] = rhs(1) / 6.0;
+    M[0] = M[1] = M[2] = rhs(1) * sixth;
   } else {  // two points: line
     M[0] = M[1] = 0.0;
   }
-  if (!live) return;
+  if (!live) return;  // (padding threads ran the recurrence of item (0, 0): harmless)
   const double tau0 = elapsed[b], tend = N * h;
   for (int j = 1; j <= N; ++j) {
     double tq = tau0 + j * h;
     tq = fmin(fmax(tq, 0.0), tend);
-    int k = int(tq / h);
+    int k = int(tq * inv_h);  // (the spline is C2: a knot attributed to the neighbouring piece changes nothing)
     k = k > N - 1 ? N - 1 : k;
     const double s = tq - k * h;
-    const double bk = (y[k + 1] - y[k]) / h - h * (2.0 * M[k] + M[k + 1]) / 6.0;
-    q[size_t(j) * nq] = y[k] + s * (bk + s * (0.5 * M[k] + s * ((M[k + 1] - M[k]) / (6.0 * h))));
+    const double bk = (y[k + 1] - y[k]) * inv_h - h * (2.0 * M[k] + M[k + 1]) * sixth;
+    q[size_t(j) * nq] = y[k] + s * (bk + s * (0.5 * M[k] + s * ((M[k + 1] - M[k]) * (sixth * inv_h))));
   }
   const double qi0 = q0[size_t(b) * nq + i];
   q[0] = qi0;

@@ -116,6 +116,7 @@ struct SolverBufs {
   double* stats;  // [B][stats_cap][IDTO_NUM_STATS]
   int stats_cap;
   int* status;  // [1] sticky device-side error flag (factorisation failure, active-pair overflow)
+  const double* spline_cp;  // [T+1] modified super-diagonal of the not-a-knot spline's Thomas recurrence (kernels_mpc.cu)
   // Debug trace of the contact pairs each inverse-dynamics evaluation applies forces for (idto_debug_pair_trace;
   // null otherwise): act_base [B][T][np] for tau_t of the state trajectory, act_fd [B][T][nq][4][np] for the
   // perturbed evaluations of tau_{t-1} at q_t +- dq e_i (stencil point kk = 0..3: +dq, -dq, +2dq, -2dq), -1 where
