@@ -101,6 +101,34 @@ __device__ __forceinline__ V3 quat_nplus_col(const double* q, int col) {
   return r;
 }
 
+// Velocity of joint k at step t: v_t = N+(q_t)(q_t - q_{t-1})/dt, v_0 = v_init (cc:178-191).  For a
+// quaternion joint the 3x4 block of N+ is returned in `col` (cc:1633-1647).
+__device__ __forceinline__ void joint_velocity(const SolverConsts& sc, int jt, const double* qt, const double* vinit,
+                                               int t, double* vt, V3* col) {
+  const int nq = sc.nq;
+  if (jt == IDTO_JOINT_QUAT_FLOATING) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) col[c] = quat_nplus_col(qt, c);
+    if (t == 0) {
+      for (int j = 0; j < 6; ++j) vt[j] = vinit[j];
+    } else {
+      const double* qm = qt - nq;
+      V3 acc = {0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double d = qt[c] - qm[c];
+        acc.x += col[c].x * d, acc.y += col[c].y * d, acc.z += col[c].z * d;
+      }
+      vt[0] = acc.x / sc.dt, vt[1] = acc.y / sc.dt, vt[2] = acc.z / sc.dt;
+      for (int j = 0; j < 3; ++j) vt[3 + j] = (qt[4 + j] - qm[4 + j]) / sc.dt;
+    }
+  } else {
+    const int n = jt == IDTO_JOINT_PLANAR ? 3 : 1;
+    for (int j = 0; j < n; ++j) vt[j] = t == 0 ? vinit[j] : (qt[j] - qt[j - nq]) / sc.dt;
+  }
+}
+
+
 __device__ __forceinline__ void hinge_map(int jtype, V3 axis, const double* x, V3* wF, V3* vF) {
   switch (jtype) {
     case IDTO_JOINT_REVOLUTE: *wF = x[0] * axis, *vF = {0, 0, 0}; break;

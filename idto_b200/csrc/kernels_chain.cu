@@ -235,14 +235,20 @@ __global__ void __launch_bounds__(320, 1) k_partials_chain(DevModel dm, SolverCo
   }
 }
 
-// tau_t = ID(q_{t+1}, v_{t+1}, a_t): one CG-lane group per (b, t).
+// One CG-lane group per (b, t): everything the trajectory-level cache holds for its step, in one launch —
+//   N+(q_{t+1}), v_{t+1} = N+ (q_{t+1} - q_t) / dt, a_t = (v_{t+1} - v_t) / dt   (cc:178-202, 1633-1647; the item t = 0
+//   also v_0 = v_init and N+(q_0)),   tau_t = ID(q_{t+1}, v_{t+1}, a_t)  (cc:204-245),   h (cc:1274-1278),
+//   its terms of the cost (cc:148-176); the group of a problem that finishes last adds the terms up in step order.
+// (Separate k_traj / k_cost launches around the latency-bound tau kernel cost 9 + 11 us and two launch gaps.)
 // STASH: additionally write the per-body records of the evaluation for the path columns (kernels_path.cu) into
 // the half of `stash` that belongs to this trajectory: ctl[b].stash_sel for the state, the other one for the
-// scratch trajectory (k_trust_update flips stash_sel when it adopts the scratch trajectory).
+// scratch trajectory (k_trust_final flips stash_sel when it adopts the scratch trajectory).
 template <int CG, int NLEV, bool STASH = false>
 __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc, TrajBuf tb, double* __restrict__ stash,
-                                                   size_t stash_half, int scratch,
-                                                   const ProbCtl* __restrict__ ctl, int force, int* act_base) {
+                                                   size_t stash_half, int scratch, ProbCtl* __restrict__ ctl, int force,
+                                                   int* act_base, const double* __restrict__ v_init,
+                                                   const double* __restrict__ q_nom, const double* __restrict__ v_nom,
+                                                   double* __restrict__ part, int* __restrict__ cnt, int clear_flag) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int T = sc.T, nq = sc.nq, nv = sc.nv;
   const int groups = blockDim.x / CG, grp = threadIdx.x / CG, c = threadIdx.x % CG;
@@ -257,18 +263,60 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
   double* base = reinterpret_cast<double*>(smem + model_smem_bytes(dm));
   stage_model(dm, si, sd, bar);
   const CModel C = make_cmodel(dm, si, sd);
-  const int gd = cgroup_doubles(dm, nv, 1);
+  const int gd = cgroup_doubles(dm, nv, 3);
   double* gbase = base + size_t(grp) * gd;
   const EvalSmem S = make_ceval(dm, gbase);
   const PoseSmem PA = make_cpose_private(dm, gbase + ceval_doubles(dm));
   double* T0 = gbase + ceval_doubles(dm) + cpose_private_doubles(dm);
+  double* vrow = T0 + nv;    // v_{t+1}
+  double* arow = vrow + nv;  // a_t
   Perturb none;
   none.owner = -1, none.local = 0, none.sl = 0, none.quatcol = false;
   none.dq = none.cv = none.ca = 0.0, none.uv = none.ua = 1.0, none.nv3 = none.na3 = {0, 0, 0};
   if (!live) return;  // (chain_eval's warp-level primitives are scoped to the group: idle groups simply leave)
+  const unsigned gm = group_mask<CG>();
+  const double* qrow = tb.q + (size_t(b) * (T + 1) + t + 1) * nq;  // q_{t+1}
+  // ---- N+, v, a of this item: the arithmetic of k_traj (kernels_traj.cu), joint by joint ---------------------------
+  for (int k = c; k < dm.nb; k += CG) {
+    const int jt = C.M.jtype[k], q0 = C.M.qs[k], v0 = C.M.vs[k];
+    const int njv = jt == IDTO_JOINT_QUAT_FLOATING ? 6 : (jt == IDTO_JOINT_PLANAR ? 3 : 1);
+    const double* vi = v_init + size_t(b) * nv + v0;
+    double vt[6], vn[6];
+    V3 col[4];
+    joint_velocity(sc, jt, qrow - nq + q0, vi, t, vt, col);  // v_t (and N+(q_t))
+    if (t == 0) {
+      double* v = tb.v + (size_t(b) * (T + 1)) * nv + v0;
+      for (int j = 0; j < njv; ++j) v[j] = vt[j];
+      if (jt == IDTO_JOINT_QUAT_FLOATING) {
+        double* Np = tb.Nplus + (size_t(b) * (T + 1)) * nv * nq;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          double* dst = Np + size_t(q0 + cc) * nv + v0;
+          dst[0] = col[cc].x, dst[1] = col[cc].y, dst[2] = col[cc].z;
+        }
+      }
+    }
+    joint_velocity(sc, jt, qrow + q0, vi, t + 1, vn, col);  // v_{t+1} and N+(q_{t+1})
+    double* v = tb.v + (size_t(b) * (T + 1) + t + 1) * nv + v0;
+    double* a = tb.a + (size_t(b) * T + t) * nv + v0;
+    for (int j = 0; j < njv; ++j) {
+      const double aj = (vn[j] - vt[j]) / sc.dt;
+      v[j] = vn[j], a[j] = aj;
+      vrow[v0 + j] = vn[j], arow[v0 + j] = aj;
+    }
+    if (jt == IDTO_JOINT_QUAT_FLOATING) {
+      double* Np = tb.Nplus + (size_t(b) * (T + 1) + t + 1) * nv * nq;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        double* dst = Np + size_t(q0 + cc) * nv + v0;
+        dst[0] = col[cc].x, dst[1] = col[cc].y, dst[2] = col[cc].z;
+      }
+    }
+  }
+  __syncwarp(gm);
+  // ---- tau_t ---------------------------------------------------------------------------------------------------
   double* rec = STASH ? stash + size_t(ctl[b].stash_sel ^ scratch) * stash_half + (size_t(b) * T + t) * dm.nb * kStashDoubles
                       : nullptr;
-  const double* qrow = tb.q + (size_t(b) * (T + 1) + t + 1) * nq;
   PairWalk pw;
   if (dm.prune && tb.near) {
     // what a finite-difference perturbation of one coordinate (|dq| <= 2 sqrt(eps) max(1,|q_i|), cc:506, 763) can
@@ -279,11 +327,55 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
     pw.margin = 4e-7 * qmax * (dm.reach + dm.nb * qmax);
   }
   if (act_base) pw.act_out = act_base + (size_t(b) * T + t) * dm.np;
-  chain_eval<CG, NLEV, kEvalFull, STASH>(C, sc, PA, S, c, qrow, tb.v + (size_t(b) * (T + 1) + t + 1) * nv,
-                                         tb.a + (size_t(b) * T + t) * nv, none, T0, rec, pw);
-  __syncwarp(group_mask<CG>());
+  chain_eval<CG, NLEV, kEvalFull, STASH>(C, sc, PA, S, c, qrow, vrow, arow, none, T0, rec, pw);
+  __syncwarp(gm);
   double* tau = tb.tau + (size_t(b) * T + t) * nv;
   for (int r = c; r < nv; r += CG) tau[r] = T0[r];
+  // h (cc:1274-1278)
+  for (int j = c; j < sc.nu; j += CG) tb.h[size_t(b) * sc.nh + t * sc.nu + j] = T0[sc.unact[j]];
+  // ---- cost terms of this item (cc:148-176, diagonal weights): tau_t, and q, v of step t+1 (t = 0: also step 0) -----
+  double* pp = part + size_t(b) * (T + 1) * 4;  // [T+1][4]: position, velocity, input term of every step
+  for (int task = c; task < (t == 0 ? 5 : 3); task += CG) {
+    double cst = 0.0;
+    if (task == 2) {
+      for (int i = 0; i < nv; ++i) cst += T0[i] * sc.R[i] * T0[i];
+      pp[t * 4 + 2] = cst;
+    } else {
+      const int tt = task < 2 ? t + 1 : 0;
+      if (task == 0 || task == 3) {  // tasks 0, 3: position
+        const double* q = tb.q + (size_t(b) * (T + 1) + tt) * nq;
+        const double* qn = q_nom + (size_t(b) * (T + 1) + tt) * nq;
+        for (int i = 0; i < nq; ++i) {
+          const double e = q[i] - qn[i];
+          cst += e * (tt < T ? sc.Qq[i] : sc.Qfq[i]) * e;
+        }
+        pp[tt * 4 + 0] = cst;
+      } else {  // tasks 1, 4: velocity (v_0 = v_init)
+        const double* v = tt == 0 ? v_init + size_t(b) * nv : vrow;
+        const double* vn = v_nom + (size_t(b) * (T + 1) + tt) * nv;
+        for (int i = 0; i < nv; ++i) {
+          const double e = v[i] - vn[i];
+          cst += e * (tt < T ? sc.Qv[i] : sc.Qfv[i]) * e;
+        }
+        pp[tt * 4 + 1] = cst;
+      }
+    }
+  }
+  // ---- the group that finishes last adds the terms up (fixed order: the result does not depend on the schedule) ----
+  __threadfence();
+  __syncwarp(gm);
+  int last = 0;
+  if (c == 0) last = atomicAdd(cnt + b, 1) == T - 1 ? 1 : 0;
+  last = __shfl_sync(gm, last, (threadIdx.x & 31) / CG * CG);
+  if (last && c == 0) {
+    cnt[b] = 0;
+    __threadfence();
+    double run = 0.0;
+    for (int tt = 0; tt < T; ++tt) run += (__ldcg(pp + tt * 4) + __ldcg(pp + tt * 4 + 1)) + __ldcg(pp + tt * 4 + 2);
+    const double term = __ldcg(pp + T * 4) + __ldcg(pp + T * 4 + 1);
+    tb.cost[b] = run * sc.dt + term;
+    if (clear_flag) ctl[b].traj_dirty = 0;
+  }
 }
 
 // ---- dispatch on (chain group size, padded tree depth) ------------------------------------------------------
@@ -317,7 +409,7 @@ template <int CG, int NLEV>
 static void launch_tau_chain_cl(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch,
                                 bool force, cudaStream_t stream) {
   const int threads = 64, groups = threads / CG;  // 2560 (b,t) items x CG lanes: small CTAs reach every SM
-  const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv, 1) * 8;
+  const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv, 3) * 8;
   static bool attr_set[kMaxDevices] = {};
   if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(k_tau_chain<CG, NLEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -328,10 +420,13 @@ static void launch_tau_chain_cl(const DevModel& dm, const SolverConsts& sc, cons
   const int grid = (sc.B * sc.T + groups - 1) / groups;
   if (bf.stash)
     k_tau_chain<CG, NLEV, true><<<grid, threads, smem, stream>>>(dm, sc, tb, bf.stash, bf.stash_half, scratch ? 1 : 0,
-                                                                 bf.ctl, force, scratch ? nullptr : bf.act_base);
+                                                                 bf.ctl, force, scratch ? nullptr : bf.act_base,
+                                                                 bf.v_init, bf.q_nom, bf.v_nom, bf.part, bf.cnt,
+                                                                 scratch ? 0 : 1);
   else
     k_tau_chain<CG, NLEV><<<grid, threads, smem, stream>>>(dm, sc, tb, nullptr, 0, 0, bf.ctl, force,
-                                                           scratch ? nullptr : bf.act_base);
+                                                           scratch ? nullptr : bf.act_base, bf.v_init, bf.q_nom,
+                                                           bf.v_nom, bf.part, bf.cnt, scratch ? 0 : 1);
 }
 
 // Instantiated (lanes per evaluation, padded tree depth) pairs; anything else falls back to the
@@ -358,7 +453,7 @@ static int chain_key(const DevModel& dm) {
 int chain_min_smem_bytes(const DevModel& dm, int nv, int method) {
   const int ntau = method == IDTO_GRAD_CENTRAL4 ? 3 : 2;
   const int partials = chain_smem_bytes(dm, nv, ntau, 1, 1);  // one slot, one column per CTA
-  const int tau = model_smem_bytes(dm) + (64 / dm.cgroup) * cgroup_doubles(dm, nv, 1) * 8;
+  const int tau = model_smem_bytes(dm) + (64 / dm.cgroup) * cgroup_doubles(dm, nv, 3) * 8;
   return partials > tau ? partials : tau;
 }
 

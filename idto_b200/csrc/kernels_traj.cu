@@ -7,33 +7,6 @@ namespace idto {
 
 namespace {
 
-// Velocity of joint k at step t: v_t = N+(q_t)(q_t - q_{t-1})/dt, v_0 = v_init (cc:178-191).  For a
-// quaternion joint the 3x4 block of N+ is returned in `col` (cc:1633-1647).
-__device__ __forceinline__ void joint_velocity(const SolverConsts& sc, int jt, const double* qt, const double* vinit,
-                                               int t, double* vt, V3* col) {
-  const int nq = sc.nq;
-  if (jt == IDTO_JOINT_QUAT_FLOATING) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) col[c] = quat_nplus_col(qt, c);
-    if (t == 0) {
-      for (int j = 0; j < 6; ++j) vt[j] = vinit[j];
-    } else {
-      const double* qm = qt - nq;
-      V3 acc = {0, 0, 0};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const double d = qt[c] - qm[c];
-        acc.x += col[c].x * d, acc.y += col[c].y * d, acc.z += col[c].z * d;
-      }
-      vt[0] = acc.x / sc.dt, vt[1] = acc.y / sc.dt, vt[2] = acc.z / sc.dt;
-      for (int j = 0; j < 3; ++j) vt[3 + j] = (qt[4 + j] - qm[4 + j]) / sc.dt;
-    }
-  } else {
-    const int n = jt == IDTO_JOINT_PLANAR ? 3 : 1;
-    for (int j = 0; j < n; ++j) vt[j] = t == 0 ? vinit[j] : (qt[j] - qt[j - nq]) / sc.dt;
-  }
-}
-
 }  // namespace
 
 // One thread per (problem, step, joint): v_t, the quaternion block of N+(q_t) (the rest of N+ is the
@@ -193,6 +166,7 @@ static void launch_tau_g(const DevModel& dm, const SolverConsts& sc, const TrajB
 
 void launch_traj(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch, bool force,
                  cudaStream_t stream) {
+  if (use_chain_kernels(dm)) return;  // k_tau_chain computes v, a, N+ of its own item (launch_tau)
   const TrajBuf& tb = scratch ? bf.sc : bf.st;
   g_launch_counter += 1;
   k_traj<<<(sc.B * (sc.T + 1) * dm.nb + 127) / 128, 128, 0, stream>>>(dm, sc, tb, bf.v_init, bf.ctl, force ? 1 : 0);
@@ -201,10 +175,8 @@ void launch_traj(const DevModel& dm, const SolverConsts& sc, const SolverBufs& b
 void launch_tau(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch, bool force,
                 cudaStream_t stream) {
   const TrajBuf& tb = scratch ? bf.sc : bf.st;
-  if (use_chain_kernels(dm)) {
+  if (use_chain_kernels(dm)) {  // one launch: N+, v, a, tau, the per-body records, cost and h
     launch_tau_chain(dm, sc, bf, scratch, force, stream);
-    g_launch_counter += 1;
-    k_cost<<<sc.B, 256, 0, stream>>>(sc, tb, bf.q_nom, bf.v_nom, bf.ctl, force ? 1 : 0, scratch ? 0 : 1);
     return;
   }
   switch (dm.group) {

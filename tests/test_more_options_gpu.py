@@ -124,3 +124,24 @@ def test_trust_ratio_model_terms_match_the_explicit_matvec(monkeypatch):
         assert np.array_equal(a[:, :, 1], b[:, :, 1])                 # trust-region radii: same decisions
         assert np.max(np.abs(a[:, :, 5] - b[:, :, 5])) < 1e-6 * max(1.0, np.max(np.abs(b[:, :, 5])))  # rho
         assert _rel(a[:, :, 0], b[:, :, 0]) < 1e-9
+
+
+def test_cost_terms_of_step_zero_and_terminal_step(oracle_mod):
+    """v_0 = v_init enters the cost through (v_0 - v_nom_0)^T Qv (v_0 - v_nom_0) (cc:148-176) even though no inverse
+    dynamics is evaluated at step 0: a large v_init far from v_nom_0 makes that term dominate."""
+    from idto_b200 import capi
+    for name, kw in (("hopper", {"T": 9}), ("mini_cheetah", {"T": 7})):
+        m, dt, prob, params, guess = getattr(problems, name)(gradients_method=GRAD_FORWARD, **kw)
+        gs = capi.BatchSolver(capi.Model(m), dt, prob, params, 2)
+        oc = oracle_mod.Oracle(m, dt, prob, params)
+        q0 = np.array(guess[0], float)
+        v0 = np.linspace(2.0, 5.0, m.nv)
+        gs.reset_initial_conditions(np.stack([q0, q0]), np.stack([v0, 0 * v0]))
+        oc.reset_initial_conditions(q0, v0)
+        gs.set_q(np.array(guess))
+        oc.set_q(np.array(guess))
+        gs.eval(0)
+        oc.eval(0)
+        assert _rel(gs.get("cost")[0], oc.get("cost")) < 1e-12
+        assert gs.get("cost")[0, 0] > 1.5 * gs.get("cost")[1, 0]  # the step-0 velocity term is a large part of it
+        assert _rel(gs.get("v")[0], oc.get("v")) < 1e-12 and _rel(gs.get("h")[0], oc.get("h")) < 1e-11
