@@ -652,9 +652,10 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   if (!m || !pd || !p || !out || batch < 1 || pd->num_steps < 1 || !(pd->time_step > 0)) return IDTO_ERR_INVALID_ARG;
   if (int rc = check_device()) return rc;
   const int nq = m->nq, nv = m->nv, T = pd->num_steps, B = batch;
-  if (!is_diag(pd->Qq, nq) || !is_diag(pd->Qv, nv) || !is_diag(pd->Qf_q, nq) || !is_diag(pd->Qf_v, nv) ||
-      !is_diag(pd->R, nv)) {
-    set_last_error("only diagonal cost weights are supported by the CUDA path");
+  const bool dense_w = !is_diag(pd->Qq, nq) || !is_diag(pd->Qv, nv) || !is_diag(pd->Qf_q, nq) ||
+                       !is_diag(pd->Qf_v, nv) || !is_diag(pd->R, nv);
+  if (dense_w && !use_chain_kernels(m->dm)) {
+    set_last_error("dense (non-diagonal) cost weights need the chain-lane inverse-dynamics kernels");
     return IDTO_ERR_UNSUPPORTED;
   }
   if (p->linear_solver < IDTO_LINSOLVE_THOMAS || p->linear_solver > IDTO_LINSOLVE_DENSE_LDLT) return IDTO_ERR_INVALID_ARG;
@@ -775,6 +776,17 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   };
   up_diag(dQq, pd->Qq, nq), up_diag(dQv, pd->Qv, nv), up_diag(dQfq, pd->Qf_q, nq), up_diag(dQfv, pd->Qf_v, nv);
   up_diag(dR, pd->R, nv);
+  sc.dense_w = dense_w ? 1 : 0;
+  sc.QqM = sc.QvM = sc.QfqM = sc.QfvM = sc.RM = nullptr;
+  if (dense_w) {
+    auto up_full = [&](const double** dst, const double* Mx, int n) {
+      double* p = nullptr;
+      if (A.get(&p, size_t(n) * n) == cudaSuccess) cudaMemcpy(p, Mx, size_t(n) * n * sizeof(double), cudaMemcpyHostToDevice);
+      *dst = p;
+    };
+    up_full(&sc.QqM, pd->Qq, nq), up_full(&sc.QvM, pd->Qv, nv), up_full(&sc.QfqM, pd->Qf_q, nq);
+    up_full(&sc.QfvM, pd->Qf_v, nv), up_full(&sc.RM, pd->R, nv);
+  }
   cudaMemcpy(dun, m->unactuated.data(), m->unactuated.size() * sizeof(int), cudaMemcpyHostToDevice);
   cudaMemcpy(dqs, m->quat_starts.data(), m->quat_starts.size() * sizeof(int), cudaMemcpyHostToDevice);
   // broadcast the template problem to every batch element

@@ -303,6 +303,168 @@ __global__ void __launch_bounds__(kAsmThreads) k_assemble(SolverConsts sc, Solve
   }
 }
 
+
+// Dense cost weights (ProblemDefinition's MatrixXd, problem_definition.h:38-52): the general form of k_assemble,
+// one thread per entry, no tiling — every shipped example has diagonal weights and takes k_assemble.  Same
+// expressions and summation order as the reference: gradient cc:1021-1081, Hessian cc:1093-1165 (X^T (W Y) with
+// W = 2 dt Q or 2 Q_f), MakeSymmetric (penta_diagonal_matrix.cc:64-105), scale factors cc:1235-1254.
+__global__ void __launch_bounds__(128) k_assemble_dense(SolverConsts sc, SolverBufs bf, int force) {
+  extern __shared__ __align__(16) double sm[];
+  const int b = blockIdx.x / (sc.T + 1), t = blockIdx.x % (sc.T + 1);
+  if (!force && !bf.ctl[b].derivs_dirty) return;
+  const int T = sc.T, nq = sc.nq, nv = sc.nv, blk = nv * nq, tid = threadIdx.x, nt = blockDim.x;
+  const double dt = sc.dt, two_dt = 2 * dt, inv_dt = 1 / dt;
+  const size_t pb = size_t(b) * T * blk;
+  double* g = bf.g + size_t(b) * sc.n + size_t(t) * nq;
+  double* HA = bf.HA + (size_t(b) * (T + 1)) * nq * nq;
+  double* HB = bf.HB + (size_t(b) * (T + 1)) * nq * nq;
+  double* HC = bf.HC + (size_t(b) * (T + 1)) * nq * nq;
+  double* D = bf.D + size_t(b) * sc.n + size_t(t) * nq;
+  auto scale_factor = [&](int e, double hd) {
+    switch (sc.scaling_method) {
+      case IDTO_SCALING_SQRT: D[e] = fmin(1.0, 1 / sqrt(hd)); break;
+      case IDTO_SCALING_ADAPTIVE_SQRT: D[e] = fmin(D[e], 1 / sqrt(hd)); break;
+      case IDTO_SCALING_DOUBLE_SQRT: D[e] = fmin(1.0, 1 / sqrt(sqrt(hd))); break;
+      default: D[e] = fmin(D[e], 1 / sqrt(sqrt(hd))); break;
+    }
+  };
+  if (t == 0) {  // cc:1044, cc:1124: g_0 = 0, C_0 = I
+    for (int e = tid; e < nq * nq; e += nt) HC[e] = (e / nq == e % nq) ? 1.0 : 0.0;
+    for (int e = tid; e < nq; e += nt) {
+      g[e] = 0.0;
+      if (sc.scaling) scale_factor(e, 1.0);
+    }
+    return;
+  }
+  double* sblk = sm;                    // [kNumBlk][blk]   (velocity blocks already divided by dt)
+  double* wy = sblk + kNumBlk * blk;    // [5][blk]  W Y for Y = N0, P0, T0, M1, N1
+  double* prod = wy + 5 * blk;          // [8][nq * nq]
+  double* wvec = prod + 8 * nq * nq;    // [6][max(nq, nv)]  weighted error vectors of the gradient
+  const int mx = nq > nv ? nq : nv;
+  const double* Np = bf.st.Nplus + size_t(b) * (T + 1) * blk;
+  const double* src[kNumBlk];
+  src[kP0] = bf.dqp + pb + size_t(t - 1) * blk;
+  src[kN0] = Np + size_t(t) * blk;
+  src[kT0] = t < T ? bf.dqt + pb + size_t(t) * blk : nullptr;
+  src[kP1] = t < T ? bf.dqp + pb + size_t(t) * blk : nullptr;
+  src[kN1] = t < T ? Np + size_t(t + 1) * blk : nullptr;
+  src[kM1] = t < T - 1 ? bf.dqm + pb + size_t(t + 1) * blk : nullptr;
+  src[kT1] = t < T - 1 ? bf.dqt + pb + size_t(t + 1) * blk : nullptr;
+  src[kP2] = t < T - 1 ? bf.dqp + pb + size_t(t + 1) * blk : nullptr;
+  for (int k = 0; k < kNumBlk; ++k)
+    for (int e = tid; e < blk; e += nt) {
+      double x = src[k] ? src[k][e] : 0.0;
+      if (k == kN0 || k == kN1) x *= inv_dt;  // dvt_dqt = N+ / dt; dvt_dqm = -N+ / dt (sign applied below)
+      sblk[k * blk + e] = x;
+    }
+  // weights of this row (cc:1103-1107): W0 for the v_t term, W4 for the v_{t+1} term, R' for the input terms
+  const double* W0 = t < T ? sc.QvM : sc.QfvM;
+  const double s0 = t < T ? two_dt : 2.0;
+  const double* W4 = (t == T - 1) ? sc.QfvM : sc.QvM;
+  const double s4 = (t == T - 1) ? 2.0 : two_dt;
+  __syncthreads();
+  // W Y: wy[k][r][j] = sum_s W[r][s] Y[s][j]
+  const int ysrc[5] = {kN0, kP0, kT0, kM1, kN1};
+  for (int e = tid; e < 5 * blk; e += nt) {
+    const int k = e / blk, rem = e - k * blk, j = rem / nv, r = rem - j * nv;
+    const double* W = k == 0 ? W0 : (k == 4 ? W4 : sc.RM);
+    const double ws = k == 0 ? s0 : (k == 4 ? s4 : two_dt);
+    const double* Y = sblk + ysrc[k] * blk + j * nv;
+    double acc = 0.0;
+    for (int s = 0; s < nv; ++s) acc += (W[size_t(s) * nv + r] * ws) * Y[s];
+    wy[e] = acc;
+  }
+  __syncthreads();
+  // products X^T (W Y): N0'WN0, P0'WP0, T0'WT0, M1'WM1, N1'WN1, P1'WT0, T1'WM1, P2'WM1
+  const int xl[8] = {kN0, kP0, kT0, kM1, kN1, kP1, kT1, kP2}, yr[8] = {0, 1, 2, 3, 4, 2, 3, 3};
+  for (int e = tid; e < 8 * nq * nq; e += nt) {
+    const int k = e / (nq * nq), rem = e - k * nq * nq, j = rem / nq, i = rem - j * nq;
+    const double* X = sblk + xl[k] * blk + i * nv;
+    const double* Z = wy + yr[k] * blk + j * nv;
+    double acc = 0.0;
+    for (int r = 0; r < nv; ++r) acc += X[r] * Z[r];
+    prod[e] = acc;
+  }
+  // weighted error vectors of the gradient (row vectors e^T W, cc:1049-1069)
+  const double* q = bf.st.q + (size_t(b) * (T + 1) + t) * nq;
+  const double* qn = bf.q_nom + (size_t(b) * (T + 1) + t) * nq;
+  const double* v = bf.st.v + (size_t(b) * (T + 1) + t) * nv;
+  const double* vn = bf.v_nom + (size_t(b) * (T + 1) + t) * nv;
+  const double* tau = bf.st.tau + size_t(b) * T * nv;
+  for (int e = tid; e < 6 * mx; e += nt) {
+    const int k = e / mx, j = e - k * mx;
+    double acc = 0.0;
+    if (k == 0 && j < nq) {  // q~^T Qq' (Qf_q' at t = T)
+      const double* W = t < T ? sc.QqM : sc.QfqM;
+      for (int i = 0; i < nq; ++i) acc += (q[i] - qn[i]) * (W[size_t(j) * nq + i] * (t < T ? two_dt : 2.0));
+    } else if (k == 1 && j < nv) {  // v~_t^T W0
+      for (int i = 0; i < nv; ++i) acc += (v[i] - vn[i]) * (W0[size_t(j) * nv + i] * s0);
+    } else if (k == 2 && j < nv && t < T) {  // v~_{t+1}^T W4
+      for (int i = 0; i < nv; ++i) acc += (v[nv + i] - vn[nv + i]) * (W4[size_t(j) * nv + i] * s4);
+    } else if (k >= 3 && j < nv) {  // tau_{t-1}, tau_t, tau_{t+1} times R'
+      const int tt = t - 1 + (k - 3);
+      if (tt < T)
+        for (int i = 0; i < nv; ++i) acc += tau[tt * nv + i] * (sc.RM[size_t(j) * nv + i] * two_dt);
+    }
+    wvec[e] = acc;
+  }
+  __syncthreads();
+  auto P = [&](int k, int i, int j) { return prod[(k * nq + j) * nq + i]; };
+  const double* QqM = t < T ? sc.QqM : sc.QfqM;
+  const double sq = t < T ? two_dt : 2.0;
+  for (int e = tid; e < nq * nq; e += nt) {
+    const int j = e / nq, i = e % nq;
+    const int il = i >= j ? i : j, jl = i >= j ? j : i;  // penta_diagonal_matrix.cc:74-76: upper of C := lower
+    double c = QqM[size_t(jl) * nq + il] * sq;
+    c += P(0, il, jl);
+    c += P(1, il, jl);
+    if (t < T) {
+      c += P(2, il, jl);
+      if (t < T - 1) c += P(3, il, jl);
+      c += P(4, il, jl);  // dvt_dqm' W dvt_dqm: the two signs cancel
+      double bb = P(5, i, j);
+      if (t < T - 1) bb += P(6, i, j);
+      bb += -P(4, i, j);  // dvt_dqt[t+1]^T W dvt_dqm[t+1] = -(N/dt)^T W (N/dt)
+      HB[size_t(t + 1) * nq * nq + e] = bb;
+      if (t < T - 1) HA[size_t(t + 2) * nq * nq + e] = P(7, i, j);
+    }
+    HC[size_t(t) * nq * nq + e] = c;
+  }
+  for (int e = tid; e < nq; e += nt) {
+    if (sc.scaling) {
+      double hd = QqM[size_t(e) * nq + e] * sq;
+      hd += P(0, e, e);
+      hd += P(1, e, e);
+      if (t < T) {
+        hd += P(2, e, e);
+        if (t < T - 1) hd += P(3, e, e);
+        hd += P(4, e, e);
+      }
+      scale_factor(e, hd);
+    }
+    auto dotcol = [&](int k, int blkid, double sign) {  // (weighted row vector k) . column e of a block
+      const double* X = sblk + blkid * blk + e * nv;
+      double acc = 0.0;
+      for (int r = 0; r < nv; ++r) acc += wvec[k * mx + r] * (sign * X[r]);
+      return acc;
+    };
+    double gj;
+    if (t < T) {
+      gj = wvec[e];
+      gj += dotcol(1, kN0, 1.0);
+      gj += dotcol(2, kN1, -1.0);
+      gj += dotcol(3, kP0, 1.0);
+      gj += dotcol(4, kT0, 1.0);
+      if (t != T - 1) gj += dotcol(5, kM1, 1.0);
+    } else {  // cc:1074-1080
+      gj = dotcol(3, kP0, 1.0);
+      gj += wvec[e];
+      gj += dotcol(1, kN0, 1.0);
+    }
+    g[e] = gj;
+  }
+}
+
 // One CTA per (b, t): scaled bands H~ = D H D (lower bands), g~ = D g, J~ bands = rows of the ID
 // partials of the unactuated dofs times D.  With scaling off D == 1 and this is a copy.
 __global__ void __launch_bounds__(128) k_scale(SolverConsts sc, SolverBufs bf, int force) {
@@ -348,7 +510,15 @@ void launch_assemble(const DevModel& dm, const SolverConsts& sc, const SolverBuf
     cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
   g_launch_counter += 2;
-  k_assemble<<<sc.B*(sc.T + 1), kAsmThreads, smem, stream>>>(sc, bf, force ? 1 : 0, alias);
+  if (sc.dense_w) {
+    const int mx = std::max(sc.nq, sc.nv);
+    const int dsmem = ((kNumBlk + 5) * sc.nv * sc.nq + 8 * sc.nq * sc.nq + 6 * mx) * 8;
+    static bool dattr[kMaxDevices] = {};
+    if (first_use_on_device(dattr))
+      cudaFuncSetAttribute(k_assemble_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_assemble_dense<<<sc.B*(sc.T + 1), 128, dsmem, stream>>>(sc, bf, force ? 1 : 0);
+  } else
+    k_assemble<<<sc.B*(sc.T + 1), kAsmThreads, smem, stream>>>(sc, bf, force ? 1 : 0, alias);
   k_scale<<<sc.B*(sc.T + 1), 128, 0, stream>>>(sc, bf, force ? 1 : 0);
 }
 

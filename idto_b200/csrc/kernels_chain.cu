@@ -337,26 +337,46 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
   double* pp = part + size_t(b) * (T + 1) * 4;  // [T+1][4]: position, velocity, input term of every step
   for (int task = c; task < (t == 0 ? 5 : 3); task += CG) {
     double cst = 0.0;
+    // e^T W e with a dense W (problem_definition.h:38-52; column-major), accumulated row by row like Eigen's
+    // (e^T W) e
+    auto quad = [&](const double* W, int nn, auto err) {
+      double s2 = 0.0;
+      for (int j = 0; j < nn; ++j) {
+        double row = 0.0;
+        for (int i = 0; i < nn; ++i) row += err(i) * W[size_t(j) * nn + i];
+        s2 += row * err(j);
+      }
+      return s2;
+    };
     if (task == 2) {
-      for (int i = 0; i < nv; ++i) cst += T0[i] * sc.R[i] * T0[i];
+      if (sc.dense_w)
+        cst = quad(sc.RM, nv, [&](int i) { return T0[i]; });
+      else
+        for (int i = 0; i < nv; ++i) cst += T0[i] * sc.R[i] * T0[i];
       pp[t * 4 + 2] = cst;
     } else {
       const int tt = task < 2 ? t + 1 : 0;
       if (task == 0 || task == 3) {  // tasks 0, 3: position
         const double* q = tb.q + (size_t(b) * (T + 1) + tt) * nq;
         const double* qn = q_nom + (size_t(b) * (T + 1) + tt) * nq;
-        for (int i = 0; i < nq; ++i) {
-          const double e = q[i] - qn[i];
-          cst += e * (tt < T ? sc.Qq[i] : sc.Qfq[i]) * e;
-        }
+        if (sc.dense_w)
+          cst = quad(tt < T ? sc.QqM : sc.QfqM, nq, [&](int i) { return q[i] - qn[i]; });
+        else
+          for (int i = 0; i < nq; ++i) {
+            const double e = q[i] - qn[i];
+            cst += e * (tt < T ? sc.Qq[i] : sc.Qfq[i]) * e;
+          }
         pp[tt * 4 + 0] = cst;
       } else {  // tasks 1, 4: velocity (v_0 = v_init)
         const double* v = tt == 0 ? v_init + size_t(b) * nv : vrow;
         const double* vn = v_nom + (size_t(b) * (T + 1) + tt) * nv;
-        for (int i = 0; i < nv; ++i) {
-          const double e = v[i] - vn[i];
-          cst += e * (tt < T ? sc.Qv[i] : sc.Qfv[i]) * e;
-        }
+        if (sc.dense_w)
+          cst = quad(tt < T ? sc.QvM : sc.QfvM, nv, [&](int i) { return v[i] - vn[i]; });
+        else
+          for (int i = 0; i < nv; ++i) {
+            const double e = v[i] - vn[i];
+            cst += e * (tt < T ? sc.Qv[i] : sc.Qfv[i]) * e;
+          }
         pp[tt * 4 + 1] = cst;
       }
     }

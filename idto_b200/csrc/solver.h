@@ -69,6 +69,11 @@ struct SolverConsts {
   double Delta_max;
   double tol[6];
   const double *Qq, *Qv, *Qfq, *Qfv, *R;  // diagonals, device [nq]/[nv]
+  // ProblemDefinition carries dense matrices (problem_definition.h:38-52); every example's are diagonal.  When one
+  // of them is not, dense_w = 1 and the full column-major matrices below feed the general (slower) cost /
+  // gradient / Hessian code paths (k_assemble_dense, the dense branch of the cost terms).
+  int dense_w;
+  const double *QqM, *QvM, *QfqM, *QfvM, *RM;
   const int* unact;                       // device [nu]
   const int* quat_starts;                 // device [nquat]
   int nquat;

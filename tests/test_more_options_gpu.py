@@ -145,3 +145,39 @@ def test_cost_terms_of_step_zero_and_terminal_step(oracle_mod):
         assert _rel(gs.get("cost")[0], oc.get("cost")) < 1e-12
         assert gs.get("cost")[0, 0] > 1.5 * gs.get("cost")[1, 0]  # the step-0 velocity term is a large part of it
         assert _rel(gs.get("v")[0], oc.get("v")) < 1e-12 and _rel(gs.get("h")[0], oc.get("h")) < 1e-11
+
+
+@pytest.mark.parametrize("name,kw", [("hopper", {"T": 12}), ("mini_cheetah", {"T": 10}), ("spinner", {"T": 15})])
+@pytest.mark.parametrize("method", [GRAD_FORWARD, GRAD_CENTRAL])
+def test_dense_cost_weights_match_oracle(oracle_mod, name, kw, method):
+    """ProblemDefinition's weights are dense MatrixXd (problem_definition.h:38-52); every example's are diagonal.  Full
+    (and slightly non-symmetric) matrices through the general cost / gradient / Hessian path against the oracle."""
+    from idto_b200 import capi
+    m, dt, prob, params, guess = getattr(problems, name)(gradients_method=method, **kw)
+    rng = np.random.default_rng(5)
+
+    def dense(Wd, asym=0.0):
+        n = Wd.shape[0]
+        A = rng.normal(0, 1, (n, n))
+        M = np.diag(np.diag(Wd)) + 0.05 * np.mean(np.diag(Wd) + 1e-3) * (A @ A.T) / n
+        return M + asym * np.mean(np.diag(Wd) + 1e-3) * np.triu(rng.normal(0, 1, (n, n)), 1)
+
+    prob.Qq, prob.Qv, prob.R = dense(prob.Qq), dense(prob.Qv, 0.01), dense(prob.R)
+    prob.Qf_q, prob.Qf_v = dense(prob.Qf_q), dense(prob.Qf_v)
+    gs = capi.BatchSolver(capi.Model(m), dt, prob, params, 2)
+    oc = oracle_mod.Oracle(m, dt, prob, params)
+    q = np.array(guess, float)
+    q[1:] += rng.normal(0, 0.03, q[1:].shape)
+    gs.set_q(np.stack([np.array(guess, float), q]))
+    oc.set_q(q)
+    gs.eval(4)
+    oc.eval(4)
+    assert _rel(gs.get("cost")[1], oc.get("cost")) < 1e-11
+    for f, tol in (("g", 2e-6), ("H_A", 4e-6), ("H_B", 4e-6), ("H_C", 4e-6), ("D", 2e-6), ("Hs_C", 4e-6), ("gs", 2e-6)):
+        assert _rel(gs.get(f)[1], oc.get(f)) < tol, f
+    assert abs(gs.get("rho")[1, 0] - oc.get("rho")[0]) < 1e-3 * max(1.0, abs(oc.get("rho")[0]))
+    gs.set_q(np.array(guess, float))
+    oc.set_q(np.array(guess, float))
+    it, _, stats = gs.solve(4)
+    k, _, so = oc.solve(4)
+    assert np.array_equal(stats[0, :, 1], so[:, 1]) and _rel(stats[0, :, 0], so[:, 0]) < 1e-6
