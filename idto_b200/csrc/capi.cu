@@ -87,6 +87,21 @@ struct idto_solver_s {
   std::vector<cudaEvent_t> sub_done;
   cudaEvent_t ev_start = nullptr;
   bool main_dirty = false, subs_dirty = false;
+  // CUDA graph of one idto_resolve_async call (stream captured once per argument set, replayed afterwards): an
+  // MPC loop issues the same ~25 copies / launches / event operations every step
+  struct GraphKey {
+    int iters = -1;
+    size_t stats_cap = 0;
+    const void* p[10] = {};
+    bool operator==(const GraphKey& o) const {
+      return iters == o.iters && stats_cap == o.stats_cap && std::memcmp(p, o.p, sizeof(p)) == 0;
+    }
+  };
+  GraphKey gkey;
+  cudaGraphExec_t gexec = nullptr;
+  long glaunches = 0;
+  int gcalls = 0;  // calls with the current key (the first one runs eagerly: first-use attribute calls, allocations)
+  bool use_graph = true;
 };
 
 namespace {
@@ -810,6 +825,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
     return IDTO_ERR_CUDA;
   }
   s->ctl_host.resize(B);
+  if (const char* e = std::getenv("IDTO_GRAPH")) s->use_graph = std::atoi(e) != 0;
   s->launches0 = g_launch_counter;
   cudaEventCreateWithFlags(&s->ev_start, cudaEventDisableTiming);
   {
@@ -826,6 +842,7 @@ int idto_solver_destroy(idto_solver_t s) {
   cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   use_main(s);
   cudaDeviceSynchronize();
+  if (s->gexec) cudaGraphExecDestroy(s->gexec);
   for (auto st : s->sub_streams) cudaStreamDestroy(st);
   for (auto ev : s->sub_done) cudaEventDestroy(ev);
   if (s->ev_start) cudaEventDestroy(s->ev_start);
@@ -843,6 +860,8 @@ int idto_solver_set_substreams(idto_solver_t s, int n) {
   if (n > s->sc.B) n = s->sc.B;
   use_main(s);
   cudaStreamSynchronize(s->stream);
+  if (s->gexec) cudaGraphExecDestroy(s->gexec);  // the graph holds the old streams' fork / join structure
+  s->gexec = nullptr, s->gcalls = 0, s->gkey = idto_solver_s::GraphKey();
   for (auto st : s->sub_streams) cudaStreamDestroy(st);
   for (auto ev : s->sub_done) cudaEventDestroy(ev);
   s->sub_streams.clear(), s->sub_done.clear();
@@ -862,6 +881,8 @@ int idto_solver_set_stream(idto_solver_t s, void* stream) {
   if (!s) return IDTO_ERR_INVALID_ARG;
   cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   s->stream = static_cast<cudaStream_t>(stream);
+  if (s->gexec) cudaGraphExecDestroy(s->gexec);
+  s->gexec = nullptr, s->gcalls = 0, s->gkey = idto_solver_s::GraphKey();
   return IDTO_OK;
 }
 
@@ -1145,11 +1166,83 @@ int idto_solve(idto_solver_t s, int max_iterations, int* iters_out, int* reason_
   return solve_collect(s, max_iterations, iters_out, reason_out, stats_out);
 }
 
+static int resolve_async_enqueue(idto_solver_t s, int max_iterations, const double* q_guess, const double* q_init,
+                                 const double* v_init, const double* q_nom, const double* v_nom, double* q_out,
+                                 double* v_out, double* tau_out, int* iters_out, double* stats_out);
+
+static void drop_graph(idto_solver_t s) {
+  if (s->gexec) cudaGraphExecDestroy(s->gexec);
+  s->gexec = nullptr, s->gcalls = 0, s->gkey = idto_solver_s::GraphKey();
+}
+
 int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_guess, const double* q_init,
                        const double* v_init, const double* q_nom, const double* v_nom, double* q_out, double* v_out,
                        double* tau_out, int* iters_out, double* stats_out) {
   if (!s || max_iterations < 0) return IDTO_ERR_INVALID_ARG;
   cudaSetDevice(s->device);  // the caller may have changed the current device since creation
+  if (!s->use_graph || s->profile || s->bf.act_base)
+    return resolve_async_enqueue(s, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
+                                 iters_out, stats_out);
+  if (int rc = ensure_stats(s, size_t(max_iterations))) return rc;  // (allocates: not inside a capture)
+  idto_solver_s::GraphKey key;
+  key.iters = max_iterations, key.stats_cap = s->stats_cap;
+  const void* ptrs[10] = {q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out, iters_out, stats_out};
+  std::memcpy(key.p, ptrs, sizeof(ptrs));
+  if (!(key == s->gkey)) {
+    drop_graph(s);
+    s->gkey = key;
+  }
+  if (s->gexec) {  // replay
+    use_main(s);
+    IDTO_CUDA_CHECK(cudaGraphLaunch(s->gexec, s->stream));
+    g_launch_counter += s->glaunches;
+    return IDTO_OK;
+  }
+  if (s->gcalls++ == 0)  // first call with these arguments: eager
+    return resolve_async_enqueue(s, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
+                                 iters_out, stats_out);
+  // second call: capture the same enqueue sequence (the sub-batch streams fork from and join into the caller's
+  // stream through events, which puts them into the capture), instantiate, launch
+  use_main(s);
+  cudaStream_t cs = s->stream;
+  cudaStream_t own = nullptr;
+  if (cs == nullptr) {  // the legacy default stream cannot be captured: capture on a private one, replay on `stream`
+    IDTO_CUDA_CHECK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+    s->stream = own;
+  }
+  const long l0 = g_launch_counter;
+  cudaGraph_t graph = nullptr;
+  int rc = IDTO_OK;
+  if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    rc = IDTO_ERR_CUDA;
+  } else {
+    s->main_dirty = true;
+    rc = resolve_async_enqueue(s, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
+                               iters_out, stats_out);
+    use_main(s);  // joins the sub-batch streams
+    if (cudaStreamEndCapture(s->stream, &graph) != cudaSuccess || !graph) rc = rc ? rc : IDTO_ERR_CUDA;
+  }
+  s->stream = cs;
+  if (own) cudaStreamDestroy(own);
+  s->glaunches = g_launch_counter - l0;
+  if (rc == IDTO_OK && cudaGraphInstantiate(&s->gexec, graph, 0) != cudaSuccess) rc = IDTO_ERR_CUDA;
+  if (graph) cudaGraphDestroy(graph);
+  if (rc != IDTO_OK) {  // capture is not available here: stay eager from now on
+    cudaGetLastError();
+    drop_graph(s);
+    s->use_graph = false;
+    g_launch_counter = l0;
+    return resolve_async_enqueue(s, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
+                                 iters_out, stats_out);
+  }
+  IDTO_CUDA_CHECK(cudaGraphLaunch(s->gexec, s->stream));
+  s->main_dirty = true;
+  return IDTO_OK;
+}
+
+static int resolve_async_enqueue(idto_solver_t s, int max_iterations, const double* q_guess, const double* q_init,
+                                 const double* v_init, const double* q_nom, const double* v_nom, double* q_out,
+                                 double* v_out, double* tau_out, int* iters_out, double* stats_out) {
   const SolverConsts& c = s->sc;
   const size_t T1 = c.T + 1, B = c.B;
   if (multi(s)) {
