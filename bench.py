@@ -146,6 +146,9 @@ def main():
                     help="weak: --batch problems per GPU; strong: --batch problems split over the GPUs "
                          "(BASELINE config 4: 'batch=64 MPC solves across 1/2/4/8 GPUs')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
+                    help="cold-L2 protocol between timed steps: 'rotate' = inputs larger than L2 (several resident "
+                         "batches take turns, one batch per step), 'flush' = a 160 MiB memset before every step")
     args = ap.parse_args()
     method = GRAD_CENTRAL if args.method == "central" else GRAD_FORWARD
     rank = int(os.environ.get("RANK", "0"))
@@ -167,8 +170,7 @@ def main():
                           + f", 1 iteration per step, gradients={args.method}_differences, equality_constraints=on, "
                             "scaling=double_sqrt",
               "model": m.name, "nq": m.nq, "nv": m.nv, "T": T, "batch_per_gpu": B, "global_batch": B * world,
-              "l2": "flushed before every step: a 160 MiB memset (L2 = 126 MB) on the solver's stream, ordered after "
-                    "the previous step and before the next on every internal stream, inside the timed region"}
+              "l2": None}
 
     if args.impl == "reference":
         if rank != 0:
@@ -182,7 +184,7 @@ def main():
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return
 
     import torch
@@ -194,7 +196,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     model = capi.Model(m)
+    free0 = torch.cuda.mem_get_info()[0]
     gs = capi.BatchSolver(model, dt, prob, params, B)
+    state_bytes = max(free0 - torch.cuda.mem_get_info()[0], 1)  # HBM held by one resident batch
     # batch element b of rank r is problem r*B + b of the global job
     from idto_b200.sharding import shard_slice
     q0, v0, qg = problems.perturbed_batch(m, prob, B * world)
@@ -202,6 +206,33 @@ def main():
     q0, v0, qg = q0[sl], v0[sl], qg[sl]
     gs.reset_initial_conditions(q0, v0)
     gs.set_q(qg)
+    # Cold L2 between timed steps.  'rotate': inputs larger than L2 — NSETS resident copies of the batch (same
+    # problems, separate HBM) take turns, ONE batch per step, steps serialised on the stream; by the time a copy is
+    # used again the others have pushed more than two L2 capacities through the cache.  'flush': one copy and a
+    # 160 MiB memset (L2 = 126 MB) in stream order before every step, inside the timed region.
+    L2_BYTES = 126e6
+    nsets = 1
+    if args.l2 == "rotate":
+        nsets = max(3, int(np.ceil(2.5 * L2_BYTES / state_bytes)) + 1)
+        if nsets > 48:  # tiny problems: too many copies; fall back to the memset
+            nsets, args.l2 = 1, "flush"
+    sets = [gs]
+    for _ in range(nsets - 1):
+        g2 = capi.BatchSolver(model, dt, prob, params, B)
+        g2.reset_initial_conditions(q0, v0)
+        g2.set_q(qg)
+        sets.append(g2)
+    config["l2"] = (f"inputs larger than L2: {nsets} resident copies of the batch ({state_bytes / 1e6:.0f} MB of solver "
+                    f"state each, L2 = 126 MB) take turns, one batch per step, steps serialised"
+                    if args.l2 == "rotate" else
+                    "flushed before every step: a 160 MiB memset (L2 = 126 MB) on the solver's stream, ordered after "
+                    "the previous step and before the next on every internal stream, inside the timed region")
+    step_no = [0]
+
+    def next_set():
+        g = sets[step_no[0] % nsets]
+        step_no[0] += 1
+        return g
 
     def barrier():
         torch.cuda.synchronize()
@@ -216,25 +247,26 @@ def main():
     # per-step working set, ~110 MB of bands / KKT sweep / partials, would otherwise fit the 126 MB L2).
     flush = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")  # L2 is 126 MB
 
-    def step_resident():
-        gs.flush_l2(flush.data_ptr(), flush.numel())
-        gs.invalidate()
-        gs.resolve_async(1)  # no host pointers: everything stays in HBM, nothing synchronises
+    def step_resident(g=None):
+        g = g or next_set()
+        if args.l2 == "flush":
+            g.flush_l2(flush.data_ptr(), flush.numel())
+        g.invalidate()
+        g.resolve_async(1)  # no host pointers: everything stays in HBM, nothing synchronises
+        g.fence()           # joins the internal streams: the next step (another copy) starts after this one
 
     # clocks / throttle reasons are sampled every 20 ms from the warm-up to the end of the end-to-end region (the
     # timed regions sit inside that window, back to back, all of it under load)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(warmup):
+    for _ in range(max(warmup, 2 * nsets)):  # (every copy captures its CUDA graph on its second call)
         step_resident()
-    gs.fence()
     barrier()
-    l0 = gs.launch_count()
+    l0 = gs.launch_count()  # (the counter is process-wide: launches of every copy)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step_resident()
-    gs.fence()
     e1.record()
     barrier()
     launches = gs.launch_count() - l0
@@ -258,12 +290,14 @@ def main():
     d2h = (oq.numel() + ov.numel() + ot.numel() + ost.numel()) * 8
 
     def step_e2e():
-        gs.flush_l2(flush.data_ptr(), flush.numel())
-        gs.mpc_advance(hel_np, hq0_np, hv0_np)  # H2D of the measured state; guess shifted on the device
-        gs.resolve_async(1, q_out=oq.data_ptr(), v_out=ov.data_ptr(), tau_out=ot.data_ptr(), stats_out=ost.data_ptr())
-        gs.synchronize()
+        g = next_set()
+        if args.l2 == "flush":
+            g.flush_l2(flush.data_ptr(), flush.numel())
+        g.mpc_advance(hel_np, hq0_np, hv0_np)  # H2D of the measured state; guess shifted on the device
+        g.resolve_async(1, q_out=oq.data_ptr(), v_out=ov.data_ptr(), tau_out=ot.data_ptr(), stats_out=ost.data_ptr())
+        g.synchronize()
 
-    for _ in range(warmup):
+    for _ in range(max(warmup, 2 * nsets)):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
@@ -279,7 +313,8 @@ def main():
     # ---- roofline of the dominant kernel (ID partials), CUDA events on the launching stream --------
     gs.profile_enable(True)
     for _ in range(5):
-        step_resident()
+        gs.flush_l2(flush.data_ptr(), flush.numel())  # (stage times: one copy, cold L2 by memset)
+        step_resident(gs)
     gs.synchronize()
     stage_ms = {}
     for name in ("id_partials", "trajectory", "assemble", "factor", "lagrange", "dogleg", "trajectory_scratch",
@@ -341,9 +376,17 @@ def main():
             val, cms, cores, sample = cpu_arm(method, 2, 1, nprob=B, name=args.workload)
             line["cpu_baseline"] = {"value": val, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample,
                                     "ms_per_step": cms}
-        print(json.dumps(line))
+        out_line = json.dumps(line)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0:
+        # printed last (after the process group is gone) and pushed through the file descriptor right away
+        sys.stdout.write(out_line + "\n")
+        sys.stdout.flush()
+        try:
+            os.fsync(sys.stdout.fileno())
+        except OSError:
+            pass
 
 
 if __name__ == "__main__":
