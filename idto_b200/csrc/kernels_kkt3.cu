@@ -72,6 +72,10 @@ __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src_gm
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void helper_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory"); }
+// (release: the stores of the calling lane before it are visible to whoever observes the completed phase)
+__device__ __forceinline__ void lu_signal(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // 1/x to ~1 ulp without the division subroutine: MUFU.RCP64H seed (>= 20 bits) + two Newton steps.
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -135,7 +139,7 @@ __device__ __forceinline__ void lu_search(double xc, int c, int lane, double* Uc
 // The pivot row reaches the other rows through shuffles (2 SHFL per column).
 template <int KB, int C0>
 __device__ __forceinline__ void lu_segment(double (&g)[KB], int lane, double* Uc, double* invc, int* piv, double* Lm,
-                                           double* prow, double* dump, LuState& s) {
+                                           double* prow, double* dump, uint64_t* bars, LuState& s) {
   constexpr int LD = (KB + 1) & ~1;
   constexpr int W = KB - 1 - C0;  // live columns right of the pivot column at the start of the segment
   constexpr int C1 = C0 + kSeg < KB ? C0 + kSeg : KB;
@@ -150,15 +154,20 @@ __device__ __forceinline__ void lu_segment(double (&g)[KB], int lane, double* Uc
 #pragma unroll
     for (int j = 2; j <= W; ++j) g[j - 1] = fma(-m, __shfl_sync(kFull, g[j], p), g[j]);
     g[0] = nxt;
+#ifndef IDTO_KKT3_NOPIPE
+    // step c + 1 is published (pivot row, its U column and reciprocal; the multipliers of steps 0..c): the threads
+    // that carry the right-hand-side columns may take it (every lane arrives: no branch in this loop)
+    lu_signal(bars + (c + 1 < KB ? c + 1 : KB));
+#endif
   }
-  if constexpr (C1 < KB) lu_segment<KB, C1>(g, lane, Uc, invc, piv, Lm, prow, dump, s);
+  if constexpr (C1 < KB) lu_segment<KB, C1>(g, lane, Uc, invc, piv, Lm, prow, dump, bars, s);
 }
 #else
 // The pivot row reaches the other rows through shared memory: the pivot lane stores its live columns (16 bytes per
 // instruction) into prow[c & 1][.], everybody loads them back as broadcasts.
 template <int KB, int C0>
 __device__ __forceinline__ void lu_segment(double (&g)[KB], int lane, double* Uc, double* invc, int* piv, double* Lm,
-                                           double* prow, double* dump, LuState& s) {
+                                           double* prow, double* dump, uint64_t* bars, LuState& s) {
   constexpr int LD = (KB + 1) & ~1;
   constexpr int W = KB - 1 - C0;
   constexpr int C1 = C0 + kSeg < KB ? C0 + kSeg : KB;
@@ -190,8 +199,11 @@ __device__ __forceinline__ void lu_segment(double (&g)[KB], int lane, double* Uc
       if (2 + 2 * q <= W) g[1 + 2 * q] = fma(-m, v.y, g[2 + 2 * q]);
     }
     g[0] = nxt;
+#ifndef IDTO_KKT3_NOPIPE
+    lu_signal(bars + (c + 1 < KB ? c + 1 : KB));
+#endif
   }
-  if constexpr (C1 < KB) lu_segment<KB, C1>(g, lane, Uc, invc, piv, Lm, prow, dump, s);
+  if constexpr (C1 < KB) lu_segment<KB, C1>(g, lane, Uc, invc, piv, Lm, prow, dump, bars, s);
 }
 #endif
 
@@ -282,6 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   __shared__ int s_fail;
   __shared__ int s_ord[64];
   __shared__ int s_piv[32];
+  __shared__ __align__(8) uint64_t s_lubar[32];  // [c] "step c of the LU is published", one phase per block row
   const int b = blockIdx.x >> 1, dir = blockIdx.x & 1;
   if (!force && !bf.ctl[b].derivs_dirty) return;  // same decision in both CTAs of the cluster
   cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
@@ -325,48 +338,103 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   double* xint = bf.tmp2 + size_t(b) * sc.n;  // interface solution (x_mid, x_mid+1): 2*kb doubles (n >= 2*kb)
   for (int e = tid; e < kSweepDoubles; e += kThreads) sm[e] = 0.0;
   if (tid == 0) s_fail = 0;
+  if (tid < 32) mbar_init(s_lubar + tid, 32);  // every lane of the LU warp arrives
   __syncthreads();
   KT_DECL
 
   // Blocks of the row visited at step n.  `issue` reads them into registers (independent loads, all in flight at
   // once), `commit` stores them to raw[n & 1] later: the loads of row n+2 fly while the helpers multiply.
-  constexpr int NEH = (kk + kHelpers - 1) / kHelpers;  // elements per helper thread
-  constexpr int NEA = (kk + kThreads - 1) / kThreads;  // elements per thread when all threads load
-  auto issue_row = [&](int n, int t0, int nt, auto& v, double& bv) {
-    constexpr int NE = std::extent<std::remove_reference_t<decltype(v)>>::value;
+  // The loads walk the SOURCE arrays (five nq x nq blocks of the scaled Hessian bands, five nu x nq blocks of the
+  // scaled Jacobian bands: contiguous, coalesced, one add per address); commit scatters them into the five kb x kb
+  // blocks of the KKT row (the blocks in front of the diagonal are transposes).  Entries no source covers are the
+  // structural zeros of the time-major ordering: they stay zero from the initial fill.
+  const int nqq = nq * nq, nuk = kb - nq, njq = nuk * nq;
+  // slots of raw[.]: back-2, back-1, diag, front-1, front-2 along the direction of the sweep
+  const int sl_m1 = dir == 0 ? 1 : 3, sl_p1 = dir == 0 ? 3 : 1, sl_m2 = dir == 0 ? 0 : 4, sl_p2 = dir == 0 ? 4 : 0;
+  auto issue_row = [&](int n, int t0, int nt, auto& vh, auto& vj, double& bv) {
+    constexpr int NH = std::extent<std::remove_reference_t<decltype(vh)>>::value;
+    constexpr int NJ = std::extent<std::remove_reference_t<decltype(vj)>>::value;
     bv = 0.0;
     if (n >= nsteps) return;
     const int i = first + sgn * n;
-    const bool hb1 = n >= 1, hb2 = n >= 2;
-    const bool hf1 = dir == 0 ? (i + 1 <= N) : (i - 1 >= 0);
-    const bool hf2 = dir == 0 ? (i + 2 <= N) : (i - 2 >= 0);
+    const bool vm1 = i >= 1, vm2 = i >= 2, vp1 = i + 1 <= N, vp2 = i + 2 <= N;
+    const double* pC = V.SC + size_t(i) * nqq;
+    const double* pB = V.SB + size_t(i) * nqq;          // block (i, i-1)
+    const double* pB1 = V.SB + size_t(i + 1) * nqq;     // block (i+1, i): transposed into (i, i+1)
+    const double* pA = V.SA + size_t(i) * nqq;          // block (i, i-2)
+    const double* pA2 = V.SA + size_t(i + 2) * nqq;     // block (i+2, i)
 #pragma unroll
-    for (int k = 0; k < NE; ++k) {
+    for (int k = 0; k < NH; ++k) {
       const int e = t0 + k * nt;
-      const int c = e / kb, rr = e - c * kb;
-      const bool ok = e < kk;
-      v[k][0] = ok && hb2 ? kkt_blk(V, i, i - 2 * sgn, rr, c) : 0.0;
-      v[k][1] = ok && hb1 ? kkt_blk(V, i, i - sgn, rr, c) : 0.0;
-      v[k][2] = ok ? kkt_C(V, i, rr, c) : 0.0;
-      v[k][3] = ok && hf1 ? kkt_blk(V, i, i + sgn, rr, c) : 0.0;
-      v[k][4] = ok && hf2 ? kkt_blk(V, i, i + 2 * sgn, rr, c) : 0.0;
+      const bool ok = e < nqq;
+      vh[k][0] = ok ? pC[e] : 0.0;
+      vh[k][1] = ok && vm1 ? pB[e] : 0.0;
+      vh[k][2] = ok && vp1 ? pB1[e] : 0.0;
+      vh[k][3] = ok && vm2 ? pA[e] : 0.0;
+      vh[k][4] = ok && vp2 ? pA2[e] : 0.0;
+    }
+    const double* jP = V.Jp + (ptrdiff_t(i) - 1) * njq;   // rows (nq+u) / columns (nq+u) of the diagonal block
+    const double* jT0 = V.Jt + (ptrdiff_t(i) - 1) * njq;  // rows nq+u of block (i, i-1)
+    const double* jT1 = V.Jt + ptrdiff_t(i) * njq;        // columns nq+u of block (i, i+1)
+    const double* jM0 = V.Jm + (ptrdiff_t(i) - 1) * njq;  // rows nq+u of block (i, i-2)
+    const double* jM1 = V.Jm + (ptrdiff_t(i) + 1) * njq;  // columns nq+u of block (i, i+2)
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      const int e = t0 + k * nt;
+      const bool ok = e < njq;
+      vj[k][0] = ok && vm1 ? jP[e] : 0.0;
+      vj[k][1] = ok && vm1 ? jT0[e] : 0.0;
+      vj[k][2] = ok && vp1 ? jT1[e] : 0.0;
+      vj[k][3] = ok && vm2 ? jM0[e] : 0.0;
+      vj[k][4] = ok && vp2 ? jM1[e] : 0.0;
     }
     if (t0 < kb) bv = t0 < nq ? -gs[i * nq + t0] : (i >= 1 ? -h[(i - 1) * sc.nu + (t0 - nq)] : 0.0);
   };
-  auto commit_row = [&](int n, int t0, int nt, const auto& v, double bv) {
-    constexpr int NE = std::extent<std::remove_reference_t<decltype(v)>>::value;
+  // (dn, dt: where element k of the calling thread goes in a block and in its transpose; fixed for the whole sweep)
+  auto commit_row = [&](int n, int t0, int nt, const auto& vh, const auto& vj, double bv, const auto& hdn,
+                        const auto& hdt, const auto& jdn, const auto& jdt) {
+    constexpr int NH = std::extent<std::remove_reference_t<decltype(vh)>>::value;
+    constexpr int NJ = std::extent<std::remove_reference_t<decltype(vj)>>::value;
     if (n >= nsteps) return;
+    const int i = first + sgn * n;
     double* dst = raw + (n & 1) * 5 * kl;
 #pragma unroll
-    for (int k = 0; k < NE; ++k) {
-      const int e = t0 + k * nt;
-      const int c = e / kb, rr = e - c * kb, o = c * LD + rr;
-      if (e < kk) {
-#pragma unroll
-        for (int q = 0; q < 5; ++q) dst[q * kl + o] = v[k][q];
+    for (int k = 0; k < NH; ++k) {
+      if (t0 + k * nt < nqq) {
+        dst[2 * kl + hdn[k]] = vh[k][0];
+        dst[sl_m1 * kl + hdn[k]] = vh[k][1];
+        dst[sl_p1 * kl + hdt[k]] = vh[k][2];
+        dst[sl_m2 * kl + hdn[k]] = vh[k][3];
+        dst[sl_p2 * kl + hdt[k]] = vh[k][4];
       }
     }
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      if (t0 + k * nt < njq) {
+        dst[2 * kl + jdn[k]] = vj[k][0];
+        dst[2 * kl + jdt[k]] = vj[k][0];
+        dst[sl_m1 * kl + jdn[k]] = vj[k][1];
+        dst[sl_p1 * kl + jdt[k]] = vj[k][2];
+        dst[sl_m2 * kl + jdn[k]] = vj[k][3];
+        dst[sl_p2 * kl + jdt[k]] = vj[k][4];
+      }
+    }
+    if (t0 < nuk) dst[2 * kl + (nq + t0) * LD + nq + t0] = i == 0 ? 1.0 : 0.0;  // dummy lambda_{-1}
     if (t0 < kb) rawb[(n & 1) * LD + t0] = bv;
+  };
+  auto make_maps = [&](int t0, int nt, auto& hdn, auto& hdt, auto& jdn, auto& jdt) {
+    constexpr int NH = std::extent<std::remove_reference_t<decltype(hdn)>>::value;
+    constexpr int NJ = std::extent<std::remove_reference_t<decltype(jdn)>>::value;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+      const int e = t0 + k * nt, c = e / nq, rr = e - c * nq;
+      hdn[k] = c * LD + rr, hdt[k] = rr * LD + c;
+    }
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      const int e = t0 + k * nt, u = e / nq, cc = e - u * nq;  // Jacobian bands are row-major (u, cc)
+      jdn[k] = cc * LD + nq + u, jdt[k] = (nq + u) * LD + cc;
+    }
   };
 
   // Products with the results of row n-2 (they do not depend on row n-1): K_n, the first part of G_n and of
@@ -408,16 +476,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   };
 
   {
-    double v0[NEA][5], v1[NEA][5], b0, b1;
-    issue_row(0, tid, kThreads, v0, b0);
-    issue_row(1, tid, kThreads, v1, b1);
-    commit_row(0, tid, kThreads, v0, b0);
-    commit_row(1, tid, kThreads, v1, b1);
+    constexpr int NHA = (kk + kThreads - 1) / kThreads, NJA = (kk / 4 + kThreads - 1) / kThreads;  // nu nq <= kb^2 / 4
+    int hdn[NHA], hdt[NHA], jdn[NJA], jdt[NJA];
+    make_maps(tid, kThreads, hdn, hdt, jdn, jdt);
+    double h0[NHA][5], j0[NJA][5], h1[NHA][5], j1[NJA][5], b0, b1;
+    issue_row(0, tid, kThreads, h0, j0, b0);
+    issue_row(1, tid, kThreads, h1, j1, b1);
+    commit_row(0, tid, kThreads, h0, j0, b0, hdn, hdt, jdn, jdt);
+    commit_row(1, tid, kThreads, h1, j1, b1, hdn, hdt, jdn, jdt);
   }
   __syncthreads();
   pre_row(0, wid, kWarps);
   __syncthreads();
   KT(0)
+
+  // the threads that prefetch the rows during the sweep, and where their elements go
+#ifndef IDTO_KKT3_NOPIPE
+  constexpr int kLoadT = kThreads - 96;  // warps 3..7
+#else
+  constexpr int kLoadT = kHelpers;       // warps 1..7
+#endif
+  constexpr int NHL = (kk + kLoadT - 1) / kLoadT, NJL = (kk / 4 + kLoadT - 1) / kLoadT;
+  const int lt = tid - (kThreads - kLoadT);
+  int hdn[NHL], hdt[NHL], jdn[NJL], jdt[NJL];
+  make_maps(lt < 0 ? 0 : lt, kLoadT, hdn, hdt, jdn, jdt);
 
   for (int n = 0; n < nsteps; ++n) {
     const int cur = n & 1, prv = cur ^ 1;
@@ -439,6 +521,105 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     KT(1)
     __syncthreads();
     KT(2)
+#ifndef IDTO_KKT3_NOPIPE
+    if (wid == 0) {
+      // ---- S2, warp 0: LU of G_n; every step is signalled to the right-hand-side threads as it is published ----
+      double g[KB];
+      KS0
+#pragma unroll
+      for (int c = 0; c < KB; ++c) g[c] = row ? Mg[cur * kl + c * LD + r] : 0.0;
+      KS(0)
+      LuState s;
+      s.done = lane >= KB, s.fail = false, s.ord = -1, s.myinv = 0.0;
+      lu_search<LD>(g[0], 0, lane, Uc, invc, s_piv, dump, s);
+      lu_signal(s_lubar);
+      lu_segment<KB, 0>(g, lane, Uc, invc, s_piv, Lm, prow, dump, s_lubar, s);
+      KS(1)
+      if (s.fail && lane == 0) s_fail = 1;
+      KS(2)
+    } else {
+      // ---- S2, warps 1..7 ---------------------------------------------------------------------------------
+      // all of them: the right-hand sides D_n - K_n Z_{n-1}, E_n, r_n;  then warps 1, 2: one right-hand-side column
+      // per thread, forward substitution in step with the LU (step c needs the pivot row p_c and the multipliers
+      // of row p_c at the steps before it: y_c = b[p_c] - sum_{k<c} Lm[k][p_c] y_k) and the backward substitution
+      // once U is complete;  warps 3..7: prefetch of row n+2, Y/Z/r of row n-1 to HBM, the products of row n+1.
+      constexpr int kPre = kThreads - 96;                    // threads of warps 3..7
+      const int hw = wid - 1;
+      const int pt = tid - 96;
+      double vh[NHL][5], vj[NJL][5], bvn = 0.0;
+      KS0
+      const double* rw = raw + cur * 5 * kl;
+      const double* Zp = Zb + prv * kl;
+      const double* rp = rb + prv * LD;
+      {
+        auto bcol = [&](int c) { return c < kb ? Zp + c * LD : rp; };
+        auto epi = [&](int rr, int c, double acc) {
+          if (c < kb)
+            My[c * LD + rr] = rw[3 * kl + c * LD + rr] - acc;
+          else
+            rv[cur * LD + rr] -= acc;
+        };
+#ifndef IDTO_KKT3_FMA
+        mma_prod<KB>(Kb + cur * kl, kb + 1, hw, kWarps - 1, lane, bcol, epi);
+#else
+        fma_prod<KB, (KB + 1 + kWarps - 2) / (kWarps - 1)>(Kb + cur * kl, kb + 1, hw, kWarps - 1, lane, bcol, epi);
+#endif
+      }
+      KS(1)
+      for (int e = tid - 32; e < kl; e += kHelpers) Mz[e] = rw[4 * kl + e];  // E_n (raw[cur] is overwritten below)
+      KS(2)
+      helper_barrier();  // the right-hand sides are complete; nobody reads raw[cur] any more
+      KS(3)
+      if (wid >= 3) {
+        issue_row(n + 2, pt, kPre, vh, vj, bvn);  // loads fly during the products below
+        if (n >= 1) store_row(n - 1, pt, kPre);
+        KS(0)
+        pre_row(n + 1, wid - 3, kWarps - 3);
+        KS(4)
+        commit_row(n + 2, pt, kPre, vh, vj, bvn, hdn, hdt, jdn, jdt);
+      } else {
+        const int t = tid - 32;  // flat column: Y (t < kb), Z (t < 2 kb), r (t == 2 kb)
+        if (t < NRHS) {
+          const double* src = t < kb ? My + t * LD : (t < 2 * kb ? Mz + (t - kb) * LD : rv + cur * LD);
+          const unsigned phase = unsigned(n & 1);
+          double y[KB];
+#pragma unroll
+          for (int c = 0; c < KB; ++c) {
+            mbar_wait(s_lubar + c, phase);
+            const int p = s_piv[c];
+            const double* lp = Lm + p;
+            double a0 = src[p], a1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < c; ++k) {
+              if (k & 1)
+                a1 = fma(-lp[k * 32], y[k], a1);
+              else
+                a0 = fma(-lp[k * 32], y[k], a0);
+            }
+            y[c] = a0 + a1;
+          }
+          // backward: unit-diagonal U~ = diag(U)^-1 U, x = U~^-1 diag(U)^-1 y
+#pragma unroll
+          for (int k = 0; k < KB; ++k) y[k] *= invc[k];
+#pragma unroll
+          for (int c = KB - 1; c >= 1; --c) {
+            const double xc = y[c];
+#pragma unroll
+            for (int k = 0; k < c; k += 2) {
+              const double2 u = *reinterpret_cast<const double2*>(Uc + c * LD + k);
+              y[k] = fma(-u.x, xc, y[k]);
+              if (k + 1 < c) y[k + 1] = fma(-u.y, xc, y[k + 1]);
+            }
+          }
+          double* dst = t < kb ? Yb + cur * kl + t * LD : (t < 2 * kb ? Zb + cur * kl + (t - kb) * LD : rb + cur * LD);
+#pragma unroll
+          for (int k = 0; k < KB; ++k) dst[k] = y[k];
+        }
+        KS(5)
+      }
+    }
+    KT(3)
+#else
     if (wid == 0) {
       // ---- S2, warp 0: LU of G_n ------------------------------------------------------------------------
       double g[KB];
@@ -449,7 +630,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       LuState s;
       s.done = lane >= KB, s.fail = false, s.ord = -1, s.myinv = 0.0;
       lu_search<LD>(g[0], 0, lane, Uc, invc, s_piv, dump, s);
-      lu_segment<KB, 0>(g, lane, Uc, invc, s_piv, Lm, prow, dump, s);
+      lu_segment<KB, 0>(g, lane, Uc, invc, s_piv, Lm, prow, dump, s_lubar, s);
 #ifdef IDTO_KKT3_SERIAL
       asm volatile("bar.sync 2, 256;" ::: "memory");  // experiment: the helpers start after the LU
 #endif
@@ -459,12 +640,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     } else {
       // ---- S2, warps 1..7: everything that does not need the LU -----------------------------------------
       const int ht = tid - 32, hw = wid - 1;
-      double vn[NEH][5], bvn;
+      double vh[NHL][5], vj[NJL][5], bvn;
 #ifdef IDTO_KKT3_SERIAL
       asm volatile("bar.sync 2, 256;" ::: "memory");
 #endif
       KS0
-      issue_row(n + 2, ht, kHelpers, vn, bvn);  // loads fly during the products below
+      issue_row(n + 2, ht, kHelpers, vh, vj, bvn);  // loads fly during the products below
       if (n >= 1) store_row(n - 1, ht, kHelpers);
       KS(0)
       const double* rw = raw + cur * 5 * kl;
@@ -492,7 +673,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       KS(3)
       helper_barrier();  // every helper is done reading raw[cur]
       KS(4)
-      commit_row(n + 2, ht, kHelpers, vn, bvn);
+      commit_row(n + 2, ht, kHelpers, vh, vj, bvn, hdn, hdt, jdn, jdt);
       KS(5)
     }
     KT(3)
@@ -543,6 +724,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
     }
     KT(6)
+#endif
     __syncthreads();
   }
   store_row(nsteps - 1, tid, kThreads);
