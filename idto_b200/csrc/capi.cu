@@ -241,6 +241,20 @@ struct Part {
   int b0;
 };
 bool multi(const idto_solver_s* s) { return s->nsub > 1 && !s->profile && !s->bf.act_base; }
+// Device-visible alias of a pinned (page-locked, mapped) host buffer; nullptr for pageable memory, which has to go
+// through cudaMemcpyAsync.  IDTO_NO_ZEROCOPY=1 keeps every transfer on the copy engines.
+template <class T>
+T* mapped_alias(T* host) {
+  static const bool off = std::getenv("IDTO_NO_ZEROCOPY") != nullptr;
+  if (!host || off) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return static_cast<T*>(a.devicePointer);
+}
 std::vector<Part> make_parts(const idto_solver_s* s) {
   std::vector<Part> parts(s->nsub);
   for (int i = 0; i < s->nsub; ++i) {
@@ -321,6 +335,31 @@ __global__ void k_set_delta(ProbCtl* ctl, const double* d, int B) {
 __global__ void k_pack_iters(const ProbCtl* ctl, int* out, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) out[b] = ctl[b].iters;
+}
+// Results of a re-solve written straight into the caller's PINNED host buffers (mapped into the device's address
+// space): one launch per sub-batch instead of four or five copy-engine transfers of ~200 KB, each with its own
+// fixed cost (48 -> ~28 us per step of 64 quadruped problems).  Outputs that are not pinned go through cudaMemcpyAsync.
+__global__ void k_export(const double* __restrict__ q, const double* __restrict__ v, const double* __restrict__ tau,
+                         const double* __restrict__ stats, const ProbCtl* __restrict__ ctl, double* __restrict__ qh,
+                         double* __restrict__ vh, double* __restrict__ tauh, double* __restrict__ sth,
+                         int* __restrict__ ith, size_t nq_tot, size_t nv_tot, size_t ntau_tot, int B, int iters,
+                         size_t stats_cap) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x, t0 = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (qh)
+    for (size_t i = t0; i < nq_tot; i += stride) qh[i] = q[i];
+  if (vh)
+    for (size_t i = t0; i < nv_tot; i += stride) vh[i] = v[i];
+  if (tauh)
+    for (size_t i = t0; i < ntau_tot; i += stride) tauh[i] = tau[i];
+  if (sth) {
+    const size_t rowlen = size_t(iters) * IDTO_NUM_STATS;
+    for (size_t i = t0; i < size_t(B) * rowlen; i += stride) {
+      const size_t b = i / rowlen, r = i - b * rowlen;
+      sth[i] = stats[b * stats_cap * IDTO_NUM_STATS + r];
+    }
+  }
+  if (ith)
+    for (size_t i = t0; i < size_t(B); i += stride) ith[i] = ctl[i].iters;
 }
 __global__ void k_fill(double* p, size_t n, double v) {
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = v;
@@ -1261,6 +1300,10 @@ static int resolve_async_enqueue(idto_solver_t s, int max_iterations, const doub
       if (dirty) k_set_ctl<<<(p.sc.B + 127) / 128, 128, 0, p.st>>>(p.bf.ctl, p.sc.B, 1, 0.0);
     }
     if (int rc = solve_enqueue(s, max_iterations)) return rc;
+    // pinned host buffers are written by one kernel per sub-batch, pageable ones by the copy engines
+    double *qm = mapped_alias(q_out), *vm = mapped_alias(v_out), *tm = mapped_alias(tau_out),
+           *sm = max_iterations > 0 ? mapped_alias(stats_out) : nullptr;
+    int* im = mapped_alias(iters_out);
     for (const Part& p : make_parts(s)) {
       const size_t o = size_t(p.b0), nb = size_t(p.sc.B);
       // solution = {q, EvalV, EvalTau} (cc:2636-2638): current after any iteration (its first stage evaluates a
@@ -1269,15 +1312,25 @@ static int resolve_async_enqueue(idto_solver_t s, int max_iterations, const doub
         launch_traj(s->model->dm, p.sc, p.bf, false, false, p.st);
         launch_tau(s->model->dm, p.sc, p.bf, false, false, p.st);
       }
-      if (q_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(q_out + o * T1 * c.nq, p.bf.st.q, nb * T1 * c.nq * 8, cudaMemcpyDeviceToHost, p.st));
-      if (v_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(v_out + o * T1 * c.nv, p.bf.st.v, nb * T1 * c.nv * 8, cudaMemcpyDeviceToHost, p.st));
-      if (tau_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(tau_out + o * c.T * c.nv, p.bf.st.tau, nb * c.T * c.nv * 8, cudaMemcpyDeviceToHost, p.st));
-      if (stats_out)
+      const size_t srow = size_t(max_iterations) * IDTO_NUM_STATS;
+      if (qm || vm || tm || sm || im) {
+        const size_t tot = nb * (T1 * c.nq + T1 * c.nv + size_t(c.T) * c.nv);
+        g_launch_counter += 1;
+        k_export<<<int(std::min<size_t>(296, (tot + 511) / 512)), 256, 0, p.st>>>(
+            p.bf.st.q, p.bf.st.v, p.bf.st.tau, p.bf.stats, p.bf.ctl, qm ? qm + o * T1 * c.nq : nullptr,
+            vm ? vm + o * T1 * c.nv : nullptr, tm ? tm + o * c.T * c.nv : nullptr, sm ? sm + o * srow : nullptr,
+            im ? im + o : nullptr, nb * T1 * c.nq, nb * T1 * c.nv, nb * c.T * c.nv, p.sc.B, max_iterations,
+            s->bf.stats_cap);
+      }
+      if (q_out && !qm) IDTO_CUDA_CHECK(cudaMemcpyAsync(q_out + o * T1 * c.nq, p.bf.st.q, nb * T1 * c.nq * 8, cudaMemcpyDeviceToHost, p.st));
+      if (v_out && !vm) IDTO_CUDA_CHECK(cudaMemcpyAsync(v_out + o * T1 * c.nv, p.bf.st.v, nb * T1 * c.nv * 8, cudaMemcpyDeviceToHost, p.st));
+      if (tau_out && !tm) IDTO_CUDA_CHECK(cudaMemcpyAsync(tau_out + o * c.T * c.nv, p.bf.st.tau, nb * c.T * c.nv * 8, cudaMemcpyDeviceToHost, p.st));
+      if (stats_out && !sm)
         IDTO_CUDA_CHECK(cudaMemcpy2DAsync(stats_out + o * max_iterations * IDTO_NUM_STATS,
                                           size_t(max_iterations) * IDTO_NUM_STATS * 8, p.bf.stats,
                                           s->bf.stats_cap * IDTO_NUM_STATS * 8,
                                           size_t(max_iterations) * IDTO_NUM_STATS * 8, nb, cudaMemcpyDeviceToHost, p.st));
-      if (iters_out) {  // rows of stats_out beyond iters_out[b] are not written by this call (early convergence)
+      if (iters_out && !im) {  // rows of stats_out beyond iters_out[b] are not written by this call (early convergence)
         k_pack_iters<<<(p.sc.B + 127) / 128, 128, 0, p.st>>>(p.bf.ctl, s->iters_dev + o, p.sc.B);
         IDTO_CUDA_CHECK(cudaMemcpyAsync(iters_out + o, s->iters_dev + o, nb * sizeof(int), cudaMemcpyDeviceToHost, p.st));
       }
@@ -1295,10 +1348,20 @@ static int resolve_async_enqueue(idto_solver_t s, int max_iterations, const doub
   if (int rc = solve_enqueue(s, max_iterations)) return rc;
   // solution = {q, EvalV, EvalTau} (cc:2636-2638); see the sub-stream branch
   if (max_iterations == 0) enqueue_trajectory(s, false, false);
-  if (q_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(q_out, s->bf.st.q, B * T1 * c.nq * 8, cudaMemcpyDeviceToHost, s->stream));
-  if (v_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(v_out, s->bf.st.v, B * T1 * c.nv * 8, cudaMemcpyDeviceToHost, s->stream));
-  if (tau_out) IDTO_CUDA_CHECK(cudaMemcpyAsync(tau_out, s->bf.st.tau, B * c.T * c.nv * 8, cudaMemcpyDeviceToHost, s->stream));
-  if (stats_out) {
+  double *qm = mapped_alias(q_out), *vm = mapped_alias(v_out), *tm = mapped_alias(tau_out),
+         *sm = max_iterations > 0 ? mapped_alias(stats_out) : nullptr;
+  int* im = mapped_alias(iters_out);
+  if (qm || vm || tm || sm || im) {
+    const size_t tot = B * (T1 * c.nq + T1 * c.nv + size_t(c.T) * c.nv);
+    g_launch_counter += 1;
+    k_export<<<int(std::min<size_t>(296, (tot + 511) / 512)), 256, 0, s->stream>>>(
+        s->bf.st.q, s->bf.st.v, s->bf.st.tau, s->bf.stats, s->bf.ctl, qm, vm, tm, sm, im, B * T1 * c.nq,
+        B * T1 * c.nv, B * c.T * c.nv, c.B, max_iterations, s->bf.stats_cap);
+  }
+  if (q_out && !qm) IDTO_CUDA_CHECK(cudaMemcpyAsync(q_out, s->bf.st.q, B * T1 * c.nq * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (v_out && !vm) IDTO_CUDA_CHECK(cudaMemcpyAsync(v_out, s->bf.st.v, B * T1 * c.nv * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (tau_out && !tm) IDTO_CUDA_CHECK(cudaMemcpyAsync(tau_out, s->bf.st.tau, B * c.T * c.nv * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (stats_out && !sm) {
     if (size_t(max_iterations) == s->stats_cap) {  // contiguous: one copy
       IDTO_CUDA_CHECK(cudaMemcpyAsync(stats_out, s->bf.stats, B * size_t(max_iterations) * IDTO_NUM_STATS * 8,
                                       cudaMemcpyDeviceToHost, s->stream));
@@ -1309,7 +1372,7 @@ static int resolve_async_enqueue(idto_solver_t s, int max_iterations, const doub
                                         s->stream));
     }
   }
-  if (iters_out) {
+  if (iters_out && !im) {
     k_pack_iters<<<(c.B + 127) / 128, 128, 0, s->stream>>>(s->bf.ctl, s->iters_dev, c.B);
     IDTO_CUDA_CHECK(cudaMemcpyAsync(iters_out, s->iters_dev, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   }
@@ -1327,11 +1390,20 @@ int idto_mpc_advance(idto_solver_t s, const double* elapsed, const double* q0, c
   double* d_q0 = d_el + B;
   double* d_v0 = d_q0 + B * c.nq;
   double* d_sel = d_v0 + B * c.nv;
-  IDTO_CUDA_CHECK(cudaMemcpyAsync(d_el, elapsed, B * 8, cudaMemcpyHostToDevice, s->stream));
-  IDTO_CUDA_CHECK(cudaMemcpyAsync(d_q0, q0, B * c.nq * 8, cudaMemcpyHostToDevice, s->stream));
-  IDTO_CUDA_CHECK(cudaMemcpyAsync(d_v0, v0, B * c.nv * 8, cudaMemcpyHostToDevice, s->stream));
-  if (q_nom_selector)
-    IDTO_CUDA_CHECK(cudaMemcpyAsync(d_sel, q_nom_selector, size_t(c.nq) * 8, cudaMemcpyHostToDevice, s->stream));
+  // pinned inputs (19 KB for 64 quadrupeds) are read by the kernel itself through their mapped aliases: four
+  // copy-engine transfers with their fixed costs are not worth it for that
+  const double *m_el = mapped_alias(elapsed), *m_q0 = mapped_alias(q0), *m_v0 = mapped_alias(v0),
+               *m_sel = mapped_alias(q_nom_selector);
+  if (m_el && m_q0 && m_v0 && (m_sel || !q_nom_selector)) {
+    d_el = const_cast<double*>(m_el), d_q0 = const_cast<double*>(m_q0), d_v0 = const_cast<double*>(m_v0);
+    d_sel = const_cast<double*>(m_sel);
+  } else {
+    IDTO_CUDA_CHECK(cudaMemcpyAsync(d_el, elapsed, B * 8, cudaMemcpyHostToDevice, s->stream));
+    IDTO_CUDA_CHECK(cudaMemcpyAsync(d_q0, q0, B * c.nq * 8, cudaMemcpyHostToDevice, s->stream));
+    IDTO_CUDA_CHECK(cudaMemcpyAsync(d_v0, v0, B * c.nv * 8, cudaMemcpyHostToDevice, s->stream));
+    if (q_nom_selector)
+      IDTO_CUDA_CHECK(cudaMemcpyAsync(d_sel, q_nom_selector, size_t(c.nq) * 8, cudaMemcpyHostToDevice, s->stream));
+  }
   if (int rc = launch_mpc_advance(c, s->bf, d_el, d_q0, d_v0, q_nom_selector ? d_sel : nullptr, s->q_init, s->v_init,
                                   s->q_nom, s->stream)) {
     set_last_error("idto_mpc_advance: horizon too long for the spline workspace");

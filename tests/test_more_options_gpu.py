@@ -181,3 +181,45 @@ def test_dense_cost_weights_match_oracle(oracle_mod, name, kw, method):
     it, _, stats = gs.solve(4)
     k, _, so = oc.solve(4)
     assert np.array_equal(stats[0, :, 1], so[:, 1]) and _rel(stats[0, :, 0], so[:, 0]) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nsub", [1, 2])
+def test_pinned_host_buffers_take_the_zero_copy_path_with_identical_results(nsub):
+    """idto_mpc_advance / idto_resolve_async with PINNED host buffers (read and written by kernels through their
+    mapped aliases) against the same calls with pageable buffers (copy engines): bit-identical outputs, for one
+    stream and for sub-batch streams, eager and graph replay (the second and third call with the same pointers)."""
+    import torch
+    from idto_b200 import capi
+    from idto_b200.types import NUM_STATS
+    m, dt, prob, params, guess = problems.hopper(T=20, gradients_method=GRAD_CENTRAL)
+    B, T1, T = 37, 21, 20
+    q0, v0, qg = problems.perturbed_batch(m, prob, B)
+    model = capi.Model(m)
+    res = {}
+    for kind in ("pageable", "pinned"):
+        def buf(shape, dtype=torch.float64):
+            t = torch.zeros(shape, dtype=dtype)
+            return t.pin_memory() if kind == "pinned" else t
+        hq0, hv0, hel = buf((B, m.nq)), buf((B, m.nv)), buf((B,))
+        hq0.numpy()[:], hv0.numpy()[:] = q0, v0
+        oq, ov, ot = buf((B, T1, m.nq)), buf((B, T1, m.nv)), buf((B, T, m.nv))
+        ost, oit = buf((B, 2, NUM_STATS)), buf((B,), torch.int32)
+        gs = capi.BatchSolver(model, dt, prob, params, B)
+        gs.set_substreams(nsub)
+        gs.reset_initial_conditions(q0, v0)
+        gs.set_q(qg)
+        gs.solve(2)
+        outs = []
+        for k in range(3):
+            hel.numpy()[:] = 0.01 * (k + 1)
+            gs.mpc_advance(hel.numpy(), hq0.numpy(), hv0.numpy())
+            gs.resolve_async(2, q_out=oq.data_ptr(), v_out=ov.data_ptr(), tau_out=ot.data_ptr(),
+                             stats_out=ost.data_ptr(), iters_out=oit.data_ptr())
+            gs.synchronize()
+            outs.append([x.numpy().copy() for x in (oq, ov, ot, ost, oit)])
+        res[kind] = outs
+        assert np.all(outs[-1][4] == 2) and np.isfinite(outs[-1][0]).all()
+    for a, b in zip(res["pageable"], res["pinned"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
