@@ -1,5 +1,8 @@
 #include <cstdlib>
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 // Chain-lane versions of the inverse-dynamics kernels (tau and the ID partials); see dynamics_chain.cuh
 // for the decomposition and kernels_partials.cu for the finite-difference scheme they share:
 //   A  tau[t-1] at q_t +- dq e_i: full evaluations (pose computed on the fly, nothing but the contact
@@ -398,12 +401,47 @@ __global__ void __launch_bounds__(128) k_tau_chain(DevModel dm, SolverConsts sc,
   }
 }
 
+// A side stream (and the two events of a fork / join) per launching stream and device, created on first use and
+// kept for the life of the process.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream& side_stream_of(cudaStream_t parent) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SideStream> all;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream& e = all[std::make_pair(dev, parent)];
+  if (!e.s) {  // (may happen while the calling thread captures a graph: creating objects is not a stream operation)
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    cudaStreamCreateWithFlags(&e.s, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&e.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e.join, cudaEventDisableTiming);
+    cudaThreadExchangeStreamCaptureMode(&mode);
+  }
+  return e;
+}
+
 // ---- dispatch on (chain group size, padded tree depth) ------------------------------------------------------
 template <int CG, int NLEV>
 static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool force,
                                      cudaStream_t stream) {
-  launch_partials_path(dm, sc, bf, force, stream);  // (the base records come from the trajectory stage)
-  if (dm.nfull == 0) return;
+  // The path columns (kernels_path.cu; the base records come from the trajectory stage) and the full columns are
+  // independent: the two kernels run side by side, the second one on a side stream forked from and joined back into
+  // `stream`.  The full-column kernel goes first so that its CTAs (one per SM, the long pole) are placed first; one
+  // path CTA then fits into the registers and shared memory each of them leaves.
+  static const bool side_by_side = [] {
+    const char* e = std::getenv("IDTO_PATH_CONCURRENT");
+    return !e || std::atoi(e) != 0;
+  }();
+  if (dm.nfull == 0 || dm.npath == 0 || !side_by_side) {
+    launch_partials_path(dm, sc, bf, force, stream);
+    if (dm.nfull == 0) return;
+  }
+  const bool fork = side_by_side && dm.npath > 0;
   const ChainLayout L = chain_layout(dm, dm.nfull, sc.nv, sc.method == IDTO_GRAD_CENTRAL4 ? 3 : 2);
   const int grid = (sc.B * sc.T + L.slots - 1) / L.slots * L.nsplit;
   g_launch_counter += 1;
@@ -417,12 +455,20 @@ static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc,
     k_partials_chain<CG, NLEV, METHOD><<<grid, L.threads, L.smem_bytes, stream>>>(dm, sc, bf, L.slots, L.nsplit,  \
                                                                                   force);                        \
   }
+  SideStream* side = fork ? &side_stream_of(stream) : nullptr;
+  if (side) cudaEventRecord(side->fork, stream);
   switch (sc.method) {
     case IDTO_GRAD_FORWARD: IDTO_LAUNCH_PC(IDTO_GRAD_FORWARD) break;
     case IDTO_GRAD_CENTRAL: IDTO_LAUNCH_PC(IDTO_GRAD_CENTRAL) break;
     default: IDTO_LAUNCH_PC(IDTO_GRAD_CENTRAL4) break;
   }
 #undef IDTO_LAUNCH_PC
+  if (side) {
+    cudaStreamWaitEvent(side->s, side->fork, 0);
+    launch_partials_path(dm, sc, bf, force, side->s);
+    cudaEventRecord(side->join, side->s);
+    cudaStreamWaitEvent(stream, side->join, 0);
+  }
 }
 
 template <int CG, int NLEV>
