@@ -136,8 +136,8 @@ def cpu_arm(method, steps, warmup, nprob=BATCH, cores=None, name="mini_cheetah")
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="idto_b200", choices=["idto_b200", "reference"])
     ap.add_argument("--method", default="central", choices=["central", "forward"])
     ap.add_argument("--batch", type=int, default=BATCH, help="problems per GPU (weak) or in the whole job (strong)")

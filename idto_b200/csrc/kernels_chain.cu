@@ -474,7 +474,11 @@ static void launch_partials_chain_cl(const DevModel& dm, const SolverConsts& sc,
 template <int CG, int NLEV>
 static void launch_tau_chain_cl(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch,
                                 bool force, cudaStream_t stream) {
-  const int threads = 64, groups = threads / CG;  // 2560 (b,t) items x CG lanes: small CTAs reach every SM
+  static const int tau_threads = [] {  // tuning knob
+    const char* e = std::getenv("IDTO_TAU_THREADS");
+    return e ? std::max(32, std::min(128, std::atoi(e) / 32 * 32)) : 64;
+  }();
+  const int threads = std::max(tau_threads, CG), groups = threads / CG;  // 2560 (b,t) items x CG lanes: small CTAs reach every SM
   const int smem = model_smem_bytes(dm) + groups * cgroup_doubles(dm, sc.nv, 3) * 8;
   static bool attr_set[kMaxDevices] = {};
   if (first_use_on_device(attr_set)) {

@@ -19,4 +19,14 @@ for name, T, method, B in (("hopper", 9, GRAD_CENTRAL, 2), ("mini_cheetah", 8, G
     gs.mpc_advance(0.5 * dt, q[:, 0], v[:, 0])
     gs.resolve_async(1)
     gs.synchronize()
+    # the same through pinned host buffers (read / written by kernels through their mapped aliases)
+    import torch
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hq0, hv0, hel = pin(q[:, 0]), pin(v[:, 0]), pin(np.full(B, 0.5 * dt))
+    oq, ov, ot = pin(np.zeros_like(q)), pin(np.zeros_like(v)), pin(np.zeros_like(tau))
+    for _ in range(3):  # eager, capture, replay
+        gs.mpc_advance(hel.numpy(), hq0.numpy(), hv0.numpy())
+        gs.resolve_async(1, q_out=oq.data_ptr(), v_out=ov.data_ptr(), tau_out=ot.data_ptr())
+        gs.synchronize()
+    assert np.isfinite(oq.numpy()).all()
     print(name, "iters", it.tolist(), "cost", stats[0, -1, 0])
