@@ -221,6 +221,7 @@ void make_view(const idto_solver_s* s, int b0, int nb, SolverConsts* scv, Solver
   v.Jm += o * T * nuq, v.Jt += o * T * nuq, v.Jp += o * T * nuq;
   v.FY += o * T1 * kb * kb, v.FZ += o * T1 * kb * kb, v.X += o * T1 * kb, v.rhs += o * nh;
   if (v.S) v.S += o * n * (3 * nq);
+  if (v.crw) v.crw += cr_workspace_doubles(b0, c.T, int(nq) + (c.eq ? c.nu : 0));
   v.pH += o * n, v.dq += o * n, v.dqH += o * n, v.tmp1 += o * n, v.tmp2 += o * n, v.red += o * 8, v.part += o * T1 * 4, v.cnt += o;
   if (v.stash) v.stash += o * T * size_t(s->model->dm.nb) * 48;
   v.ctl += o;
@@ -712,7 +713,7 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
     set_last_error("dense (non-diagonal) cost weights need the chain-lane inverse-dynamics kernels");
     return IDTO_ERR_UNSUPPORTED;
   }
-  if (p->linear_solver < IDTO_LINSOLVE_THOMAS || p->linear_solver > IDTO_LINSOLVE_DENSE_LDLT) return IDTO_ERR_INVALID_ARG;
+  if (p->linear_solver < IDTO_LINSOLVE_THOMAS || p->linear_solver > IDTO_LINSOLVE_CYCLIC_REDUCTION) return IDTO_ERR_INVALID_ARG;
   if (p->gradients_method < IDTO_GRAD_FORWARD || p->gradients_method > IDTO_GRAD_CENTRAL4) {
     set_last_error("gradients_method must be forward, central or central4 (autodiff needs Drake scalars)");
     return IDTO_ERR_UNSUPPORTED;
@@ -790,6 +791,9 @@ int idto_solver_create(idto_model_t m, const idto_problem_desc* pd, const idto_p
   const size_t kbm = size_t(nq) + sc.nu;  // KKT block size
   bf.FK = bf.FG = bf.S = nullptr;
   if (p->linear_solver == IDTO_LINSOLVE_DENSE_LDLT) alloc(&bf.S, size_t(B) * sc.n * (3 * nq));  // band storage of H~
+  bf.crw = nullptr;
+  if (p->linear_solver == IDTO_LINSOLVE_CYCLIC_REDUCTION)
+    alloc(&bf.crw, cr_workspace_doubles(B, sc.T, nq + (sc.eq ? sc.nu : 0)));
   alloc(&bf.FY, size_t(B) * (T + 1) * kbm * kbm), alloc(&bf.FZ, size_t(B) * (T + 1) * kbm * kbm);
   alloc(&bf.X, size_t(B) * (T + 1) * kbm);
   alloc(&bf.rhs, size_t(B) * nh);

@@ -291,15 +291,15 @@ __device__ __forceinline__ void path_eval(const GModel& M, const SolverConsts& s
 }  // namespace
 
 // One thread per (phase A/B/C, path column, problem, step t = 1..T, stencil point).
-// Launch bounds: three CTAs per SM = at most 168 registers per thread, so that one CTA of this kernel fits next to a
-// CTA of k_partials_chain (168 registers x 256 threads, 221 KB of shared memory) on the same SM: the two kernels are
+// At most 176 registers per thread, so that one CTA of this kernel (128 x 176 = 22 528 registers, 7 KB of shared
+// memory) fits next to a CTA of k_partials_chain (256 x 168 = 43 008 registers, 221 KB) on the same SM: the two kernels are
 // independent and run concurrently (kernels_chain.cu), this one — L2-latency bound — in the issue slots the other —
 // a chain of dependent fp64 operations — leaves idle.
-#ifndef IDTO_PATH_MINB
-#define IDTO_PATH_MINB 3
+#ifndef IDTO_PATH_MAXREG
+#define IDTO_PATH_MAXREG 176
 #endif
 template <int METHOD>
-__global__ void __launch_bounds__(128, IDTO_PATH_MINB) k_partials_path(DevModel dm, SolverConsts sc, SolverBufs bf, int force) {
+__global__ void __maxnreg__(IDTO_PATH_MAXREG) k_partials_path(DevModel dm, SolverConsts sc, SolverBufs bf, int force) {
   const int T = sc.T, nq = sc.nq, nv = sc.nv, np = dm.npath;
   // consecutive threads take consecutive (problem, step) items of the SAME column and phase: a warp runs one
   // code path with one trip count (mixing the phases in a warp serialised three instantiations: 523 us)

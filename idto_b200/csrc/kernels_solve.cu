@@ -740,7 +740,9 @@ void launch_lagrange(const DevModel& dm, const SolverConsts& sc, const SolverBuf
   g_launch_counter += 1;
   // two-sided elimination needs at least 4 block rows per half to pay off; 2*kb interface unknowns must fit n
   bool launched;
-  if (sc.linear_solver != IDTO_LINSOLVE_THOMAS && sc.T + 1 >= 8)
+  if (sc.linear_solver == IDTO_LINSOLVE_CYCLIC_REDUCTION && bf.crw)
+    launched = launch_kkt_cr(kb, sc, bf, force, stream);
+  else if (sc.linear_solver != IDTO_LINSOLVE_THOMAS && sc.T + 1 >= 8)
     launched = launch_kkt_v3(kb, sc, bf, force, stream) || launch_kkt_tw2(kb, sc, bf, force, stream) ||
                launch_kkt_twisted_dispatch<1>(kb, sc, bf, force, stream);
   else

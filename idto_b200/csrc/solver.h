@@ -121,6 +121,7 @@ struct SolverBufs {
   double* stats;  // [B][stats_cap][IDTO_NUM_STATS]
   int stats_cap;
   int* status;  // [1] sticky device-side error flag (factorisation failure, active-pair overflow)
+  double* crw;              // workspace of the cyclic-reduction solver (kernels_cr.cu), nullptr unless selected
   const double* spline_cp;  // [T+1] modified super-diagonal of the not-a-knot spline's Thomas recurrence (kernels_mpc.cu)
   // Debug trace of the contact pairs each inverse-dynamics evaluation applies forces for (idto_debug_pair_trace;
   // null otherwise): act_base [B][T][np] for tau_t of the state trajectory, act_fd [B][T][nq][4][np] for the
@@ -150,6 +151,9 @@ void launch_trust_final(const DevModel& dm, const SolverConsts& sc, const Solver
 bool launch_kkt_tw2(int kb, const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
 // third generation (kernels_kkt3.cu): single-warp LU + column-per-thread triangular solves; same contract
 bool launch_kkt_v3(int kb, const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
+// block cyclic reduction of the same system (kernels_cr.cu): linear_solver = IDTO_LINSOLVE_CYCLIC_REDUCTION
+bool launch_kkt_cr(int kb, const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);
+size_t cr_workspace_doubles(int B, int T, int kb);
 void launch_conv_check(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
 void launch_clear_dirty(const SolverConsts& sc, const SolverBufs& b, cudaStream_t stream);
 void launch_gm_matvec(const SolverConsts& sc, const SolverBufs& b, bool force, cudaStream_t stream);

@@ -15,7 +15,7 @@ _D = ctypes.POINTER(ctypes.c_double)
 
 GRAD_FORWARD, GRAD_CENTRAL, GRAD_CENTRAL4 = 0, 1, 2
 SCALING_SQRT, SCALING_ADAPTIVE_SQRT, SCALING_DOUBLE_SQRT, SCALING_ADAPTIVE_DOUBLE_SQRT = 0, 1, 2, 3
-LINSOLVE_THOMAS, LINSOLVE_TWISTED, LINSOLVE_DENSE_LDLT = 0, 1, 2
+LINSOLVE_THOMAS, LINSOLVE_TWISTED, LINSOLVE_DENSE_LDLT, LINSOLVE_CYCLIC_REDUCTION = 0, 1, 2, 3
 NUM_STATS = 10
 STAT_NAMES = ("cost", "delta", "q_norm", "dq_norm", "dqH_norm", "trust_ratio", "grad_norm", "dL_dq",
               "h_norm", "merit")

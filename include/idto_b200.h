@@ -98,7 +98,8 @@ enum { IDTO_SCALING_SQRT = 0, IDTO_SCALING_ADAPTIVE_SQRT = 1,
 /* TWISTED / THOMAS: the block penta-diagonal solver (reference: kPentaDiagonalLu) as a two-sided or a single
  * top-down sweep; DENSE_LDLT: the reference's debugging cross-check kDenseLdlt (trajectory_optimizer.cc:2088-2093):
  * the Gauss-Newton step is re-solved by a structure-agnostic LDL^T of H~. */
-enum { IDTO_LINSOLVE_THOMAS = 0, IDTO_LINSOLVE_TWISTED = 1, IDTO_LINSOLVE_DENSE_LDLT = 2 };
+enum { IDTO_LINSOLVE_THOMAS = 0, IDTO_LINSOLVE_TWISTED = 1, IDTO_LINSOLVE_DENSE_LDLT = 2,
+       IDTO_LINSOLVE_CYCLIC_REDUCTION = 3 };
 
 typedef struct {
   int max_iterations;         /* 100 */

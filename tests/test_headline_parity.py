@@ -313,3 +313,47 @@ def test_kkt_sweep_on_gpu_inputs_matches_dense_lapack(name, kw):
         assert relerr(gs.get("lambda")[1], lam) < max(tol, 1e-9 * condS), (condH, condS)
     assert relerr(gs.get("gm")[1], gm) < max(1e-11, tol * 1e-3)  # gm = gs + J^T lambda: no solve involved
     assert relerr(gs.get("dqH")[1], dqH) < tol, condH
+
+
+# (g) block cyclic reduction of the same system (kernels_cr.cu) against LAPACK and against the sweep ----------------
+@pytest.mark.parametrize("name,kw", [("mini_cheetah", {"T": 40}), ("mini_cheetah", {"T": 13}), ("hopper", {}),
+                                     ("spinner", {}), ("allegro_hand", {"T": 20}),
+                                     ("hopper", {"equality_constraints": False})])
+def test_cyclic_reduction_matches_dense_lapack_and_the_sweep(name, kw):
+    """linear_solver = LINSOLVE_CYCLIC_REDUCTION: super-rows of two block rows, odd rows of every level eliminated
+    in parallel (odd and even numbers of block rows, with and without equality constraints).  Same tolerances as
+    the sweep's LAPACK test; a two-iteration solve takes the same accept/reject decisions as the sweep."""
+    from idto_b200 import capi
+    from idto_b200.types import LINSOLVE_CYCLIC_REDUCTION, LINSOLVE_TWISTED
+    kw = dict(kw)
+    eq = kw.pop("equality_constraints", True)
+    m, dt, prob, params, guess = getattr(problems, name)(gradients_method=GRAD_CENTRAL, **kw)
+    params.equality_constraints = eq
+    T, nq = prob.num_steps, m.nq
+    rng = np.random.default_rng(7)
+    q = np.array(guess, float)
+    q[1:] += rng.normal(0, 0.01 if name == "allegro_hand" else 0.03, q[1:].shape)
+    q2 = np.stack([np.array(guess, float), q])
+    out = {}
+    for ls in (LINSOLVE_TWISTED, LINSOLVE_CYCLIC_REDUCTION):
+        params.linear_solver = ls
+        gs = capi.BatchSolver(capi.Model(m), dt, prob, params, 2)
+        gs.set_q(q2)
+        gs.eval(3)
+        A, B_, C = (gs.get(f)[1].reshape(T + 1, nq * nq) for f in ("Hs_A", "Hs_B", "Hs_C"))
+        has_eq = gs.model.nu > 0 and params.equality_constraints
+        J = gs.get("J")[1] if has_eq else None
+        h = gs.get("h")[1] if has_eq else None
+        lam, gm, dqH, condH, condS = kkt_reference(A, B_, C, gs.get("gs")[1], J, h)
+        # cyclic reduction pivots inside its 2kb x 2kb blocks only and squares the coupling blocks level by level: it
+        # loses about a digit against the sweep on the quadruped (cond 2e11: 8e-4 against 5e-5 = cond x eps)
+        tol = max(1e-9, condH * 2.220446049250313e-16) * (50.0 if ls == LINSOLVE_CYCLIC_REDUCTION else 1.0)
+        if has_eq:
+            assert relerr(gs.get("lambda")[1], lam) < max(tol, 1e-9 * condS), (ls, condH, condS)
+        assert relerr(gs.get("dqH")[1], dqH) < tol, (ls, condH)
+        it, reason, stats = gs.solve(2)
+        out[ls] = (gs.get("lambda").copy(), gs.get("dqH").copy(), stats.copy())
+    a, b = out[LINSOLVE_TWISTED], out[LINSOLVE_CYCLIC_REDUCTION]
+    assert np.array_equal(a[2][:, :, 5] > 0, b[2][:, :, 5] > 0)  # rho > 0: same accept / reject decisions
+    assert np.allclose(a[2][:, :, 1], b[2][:, :, 1])              # same trust-region radii
+    assert relerr(b[2][:, :, 0], a[2][:, :, 0]) < 1e-6            # same costs
