@@ -97,7 +97,9 @@ enum { IDTO_SCALING_SQRT = 0, IDTO_SCALING_ADAPTIVE_SQRT = 1,
 /* single top-down block-Thomas sweep, or two-sided ("twisted") elimination by a 2-CTA cluster */
 /* TWISTED / THOMAS: the block penta-diagonal solver (reference: kPentaDiagonalLu) as a two-sided or a single
  * top-down sweep; DENSE_LDLT: the reference's debugging cross-check kDenseLdlt (trajectory_optimizer.cc:2088-2093):
- * the Gauss-Newton step is re-solved by a structure-agnostic LDL^T of H~. */
+ * the Gauss-Newton step is re-solved by a structure-agnostic LDL^T of H~; CYCLIC_REDUCTION: the same block system
+ * (kPentaDiagonalLu) eliminated by parallel block cyclic reduction instead of a sweep (same results to the
+ * conditioning of the system; slower than the sweep for T <= 60 at batch 64). */
 enum { IDTO_LINSOLVE_THOMAS = 0, IDTO_LINSOLVE_TWISTED = 1, IDTO_LINSOLVE_DENSE_LDLT = 2,
        IDTO_LINSOLVE_CYCLIC_REDUCTION = 3 };
 

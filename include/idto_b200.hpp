@@ -107,7 +107,8 @@ struct ConvergenceCriteriaTolerances {
 };
 
 struct SolverParameters {
-  enum LinearSolverType { kDenseLdlt, kPentaDiagonalLu };
+  // (kCyclicReduction: this build's parallel-in-time order of kPentaDiagonalLu's elimination; not in the reference)
+  enum LinearSolverType { kDenseLdlt, kPentaDiagonalLu, kCyclicReduction };
   bool check_convergence = false;
   ConvergenceCriteriaTolerances convergence_tolerances;
   SolverMethod method{kTrustRegion};
@@ -547,6 +548,7 @@ class TrajectoryOptimizer {
     p.scaling = s.scaling, p.scaling_method = int(s.scaling_method), p.equality_constraints = s.equality_constraints;
     p.Delta0 = s.Delta0, p.Delta_max = s.Delta_max, p.check_convergence = s.check_convergence;
     if (s.linear_solver == SolverParameters::kDenseLdlt) p.linear_solver = IDTO_LINSOLVE_DENSE_LDLT;  // cc:2088-2093
+    if (s.linear_solver == SolverParameters::kCyclicReduction) p.linear_solver = IDTO_LINSOLVE_CYCLIC_REDUCTION;
     const ConvergenceCriteriaTolerances& t = s.convergence_tolerances;
     p.tol_rel_cost_reduction = t.rel_cost_reduction, p.tol_abs_cost_reduction = t.abs_cost_reduction;
     p.tol_rel_gradient_along_dq = t.rel_gradient_along_dq, p.tol_abs_gradient_along_dq = t.abs_gradient_along_dq;

@@ -137,6 +137,18 @@ int main(int argc, char** argv) {
       CHECK(std::fabs(std_.iteration_costs[k] - stats.iteration_costs[k]) < 1e-6 * std::fabs(stats.iteration_costs[k]));
   }
 
+  // kCyclicReduction (this build's parallel-in-time order of the same elimination): same iterates too
+  {
+    SolverParameters pc = params;
+    pc.max_iterations = 5, pc.linear_solver = SolverParameters::kCyclicReduction;
+    TrajectoryOptimizer<double> optc(diagram, &plant, problem, pc);
+    TrajectoryOptimizerSolution<double> sc_;
+    TrajectoryOptimizerStats<double> stc;
+    optc.Solve(q_guess, &sc_, &stc);
+    for (int k = 0; k < 5; ++k)
+      CHECK(std::fabs(stc.iteration_costs[k] - stats.iteration_costs[k]) < 1e-6 * std::fabs(stats.iteration_costs[k]));
+  }
+
   // a batch over every GPU of the process (one host thread per device, no collective): each problem equals the
   // single solve above
   {
