@@ -15,7 +15,7 @@
 
 namespace idto {
 
-long g_launch_counter = 0;
+std::atomic<long> g_launch_counter{0};
 bool use_chain_kernels(const DevModel& dm) {
   static const bool force_group = [] {
     const char* e = std::getenv("IDTO_DYNAMICS");

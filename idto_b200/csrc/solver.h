@@ -16,6 +16,8 @@
 #include <cstdint>
 
 #include "../../include/idto_b200.h"
+#include <atomic>
+
 #include "common.cuh"
 
 namespace idto {
@@ -179,6 +181,6 @@ void launch_partials_path(const DevModel& dm, const SolverConsts& sc, const Solv
 void launch_tau_chain(const DevModel& dm, const SolverConsts& sc, const SolverBufs& bf, bool scratch, bool force,
                       cudaStream_t stream);
 bool use_chain_kernels(const DevModel& dm);  // chain-lane kernels unless IDTO_DYNAMICS=group or unsupported
-extern long g_launch_counter;  // kernels launched by this library (all solvers)
+extern std::atomic<long> g_launch_counter;  // kernels launched by this library (all solvers; solvers of different devices run on different host threads)
 
 }  // namespace idto
