@@ -223,7 +223,12 @@ int idto_solve(idto_solver_t s, int max_iterations, int* iters_out, int* reason_
  * Any input pointer may be NULL to keep the device-resident value.
  * iters_out (pinned host [batch], may be NULL) receives the number of iterations recorded per problem:
  * with check_convergence a problem may stop early, and rows of stats_out beyond iters_out[b] are not
- * written by this call. */
+ * written by this call.
+ * Host buffers may be pageable or pinned.  Pinned (page-locked, mapped) buffers are read and written by kernels
+ * directly through their device aliases — no staging copies; pageable ones go through cudaMemcpyAsync.  Either way
+ * they must not be touched before idto_synchronize(), and a buffer that is passed again at the same address must
+ * still be pinned (or still be pageable): the call sequence of a given argument set is captured once (CUDA graph)
+ * and replayed. */
 int idto_resolve_async(idto_solver_t s, int max_iterations,
                        const double* q_guess, const double* q_init, const double* v_init,
                        const double* q_nom, const double* v_nom,
