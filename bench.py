@@ -13,8 +13,8 @@ guess shift), so no step is a cheap "rejected step" replay.
   value = problems * steps / device time, inputs resident in HBM.
   e2e   = the same through the public C-ABI calls an MPC loop makes (ModelPredictiveController::
           UpdateAbstractState, examples/mpc_controller.cc:43-98) with pinned HOST buffers: per step H2D of
-          the measured state (q0, v0, elapsed time) into idto_mpc_advance, which shifts the previous
-          solution on the device, then the re-solve and D2H of the solution trajectory and stats.
+          the measured state (q0, v0, elapsed time) into idto_mpc_resolve_async (= idto_mpc_advance, which shifts
+          the previous solution on the device, + the re-solve), and D2H of the solution trajectory and stats.
 """
 from __future__ import annotations
 
@@ -300,8 +300,10 @@ def main():
         g = next_set()
         if args.l2 == "flush":
             g.flush_l2(flush.data_ptr(), flush.numel())
-        g.mpc_advance(hel_np, hq0_np, hv0_np)  # H2D of the measured state; guess shifted on the device
-        g.resolve_async(1, q_out=oq.data_ptr(), v_out=ov.data_ptr(), tau_out=ot.data_ptr(), stats_out=ost.data_ptr())
+        # one MPC re-plan = one call (ModelPredictiveController::UpdateAbstractState, examples/mpc_controller.cc:43-85):
+        # measured state in (H2D), guess shifted on the device, one iteration, solution + stats out (D2H)
+        g.mpc_resolve_async(hel_np, hq0_np, hv0_np, 1, q_out=oq.data_ptr(), v_out=ov.data_ptr(),
+                            tau_out=ot.data_ptr(), stats_out=ost.data_ptr())
         g.synchronize()
 
     for _ in range(max(warmup, 2 * nsets)):

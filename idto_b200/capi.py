@@ -74,6 +74,7 @@ def lib():
         L.idto_solve.argtypes = [H, ctypes.c_int, _I, _I, _D]
         L.idto_resolve_async.argtypes = [H, ctypes.c_int] + [ctypes.c_void_p] * 8 + [_I, ctypes.c_void_p]
         L.idto_mpc_advance.argtypes = [H, _D, _D, _D, _D]
+        L.idto_mpc_resolve_async.argtypes = [H, _D, _D, _D, _D, ctypes.c_int] + [ctypes.c_void_p] * 3 + [_I, ctypes.c_void_p]
         L.idto_fence.argtypes = [H]
         L.idto_flush_l2.argtypes = [H, ctypes.c_void_p, ctypes.c_size_t]
         L.idto_debug_pair_trace.argtypes = [H, ctypes.c_int]
@@ -198,6 +199,25 @@ class BatchSolver:
         v0 = v0 if ready(v0, (self.B, self.nv)) else self._arr(v0, (self.B, self.nv))
         sel = None if q_nom_selector is None else np.ascontiguousarray(np.asarray(q_nom_selector, float).reshape(self.nq))
         _check(lib().idto_mpc_advance(self.h, _p(el), _p(q0), _p(v0), None if sel is None else _p(sel)))
+
+    def mpc_resolve_async(self, elapsed, q0, v0, max_iterations, q_nom_selector=None, q_out=None, v_out=None,
+                          tau_out=None, stats_out=None, iters_out=None):
+        """One MPC re-plan in one call (ModelPredictiveController::UpdateAbstractState, examples/mpc_controller.cc:
+        43-85): mpc_advance(elapsed, q0, v0) followed by resolve_async(max_iterations, outputs).  elapsed [batch],
+        q0 [batch, nq], v0 [batch, nv]: float64 arrays (pinned ones are read by the device directly); outputs: raw
+        host pointers (ints) or None."""
+        def ready(x, shape):
+            return isinstance(x, np.ndarray) and x.dtype == np.float64 and x.shape == shape and x.flags.c_contiguous
+
+        el = elapsed if ready(elapsed, (self.B,)) else np.ascontiguousarray(
+            np.broadcast_to(np.asarray(elapsed, float), (self.B,)))
+        q0 = q0 if ready(q0, (self.B, self.nq)) else self._arr(q0, (self.B, self.nq))
+        v0 = v0 if ready(v0, (self.B, self.nv)) else self._arr(v0, (self.B, self.nv))
+        sel = None if q_nom_selector is None else np.ascontiguousarray(np.asarray(q_nom_selector, float).reshape(self.nq))
+        it = None if iters_out is None else ctypes.cast(ctypes.c_void_p(iters_out), _I)
+        _check(lib().idto_mpc_resolve_async(self.h, _p(el), _p(q0), _p(v0), None if sel is None else _p(sel),
+                                            int(max_iterations), q_out, v_out, tau_out, it, stats_out))
+        self._mpc_keep = (el, q0, v0, sel)  # temporaries must outlive the asynchronous call
 
     def fence(self):
         _check(lib().idto_fence(self.h))

@@ -92,7 +92,7 @@ struct idto_solver_s {
   struct GraphKey {
     int iters = -1;
     size_t stats_cap = 0;
-    const void* p[10] = {};
+    const void* p[14] = {};  // host pointers of the call (10 of the re-solve, 4 of a leading MPC advance)
     bool operator==(const GraphKey& o) const {
       return iters == o.iters && stats_cap == o.stats_cap && std::memcmp(p, o.p, sizeof(p)) == 0;
     }
@@ -1209,27 +1209,42 @@ int idto_solve(idto_solver_t s, int max_iterations, int* iters_out, int* reason_
   return solve_collect(s, max_iterations, iters_out, reason_out, stats_out);
 }
 
+// host pointers of an MPC advance that leads a re-solve (idto_mpc_resolve_async); null `elapsed`: none
+struct MpcArgs {
+  const double *elapsed = nullptr, *q0 = nullptr, *v0 = nullptr, *selector = nullptr;
+};
+static int mpc_advance_enqueue(idto_solver_t s, const MpcArgs& m);
 static int resolve_async_enqueue(idto_solver_t s, int max_iterations, const double* q_guess, const double* q_init,
                                  const double* v_init, const double* q_nom, const double* v_nom, double* q_out,
                                  double* v_out, double* tau_out, int* iters_out, double* stats_out);
+static int advance_and_resolve_enqueue(idto_solver_t s, const MpcArgs& m, int max_iterations, const double* q_guess,
+                                       const double* q_init, const double* v_init, const double* q_nom,
+                                       const double* v_nom, double* q_out, double* v_out, double* tau_out,
+                                       int* iters_out, double* stats_out) {
+  if (m.elapsed)
+    if (int rc = mpc_advance_enqueue(s, m)) return rc;
+  return resolve_async_enqueue(s, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
+                               iters_out, stats_out);
+}
 
 static void drop_graph(idto_solver_t s) {
   if (s->gexec) cudaGraphExecDestroy(s->gexec);
   s->gexec = nullptr, s->gcalls = 0, s->gkey = idto_solver_s::GraphKey();
 }
 
-int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_guess, const double* q_init,
-                       const double* v_init, const double* q_nom, const double* v_nom, double* q_out, double* v_out,
-                       double* tau_out, int* iters_out, double* stats_out) {
+static int resolve_impl(idto_solver_t s, const MpcArgs& mpc, int max_iterations, const double* q_guess,
+                        const double* q_init, const double* v_init, const double* q_nom, const double* v_nom,
+                        double* q_out, double* v_out, double* tau_out, int* iters_out, double* stats_out) {
   if (!s || max_iterations < 0) return IDTO_ERR_INVALID_ARG;
   cudaSetDevice(s->device);  // the caller may have changed the current device since creation
   if (!s->use_graph || s->profile || s->bf.act_base)
-    return resolve_async_enqueue(s, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
+    return advance_and_resolve_enqueue(s, mpc, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
                                  iters_out, stats_out);
   if (int rc = ensure_stats(s, size_t(max_iterations))) return rc;  // (allocates: not inside a capture)
   idto_solver_s::GraphKey key;
   key.iters = max_iterations, key.stats_cap = s->stats_cap;
-  const void* ptrs[10] = {q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out, iters_out, stats_out};
+  const void* ptrs[14] = {q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out, iters_out, stats_out,
+                          mpc.elapsed, mpc.q0, mpc.v0, mpc.selector};
   std::memcpy(key.p, ptrs, sizeof(ptrs));
   if (!(key == s->gkey)) {
     drop_graph(s);
@@ -1242,7 +1257,7 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
     return IDTO_OK;
   }
   if (s->gcalls++ == 0)  // first call with these arguments: eager
-    return resolve_async_enqueue(s, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
+    return advance_and_resolve_enqueue(s, mpc, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
                                  iters_out, stats_out);
   // second call: capture the same enqueue sequence (the sub-batch streams fork from and join into the caller's
   // stream through events, which puts them into the capture), instantiate, launch
@@ -1260,7 +1275,7 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
     rc = IDTO_ERR_CUDA;
   } else {
     s->main_dirty = true;
-    rc = resolve_async_enqueue(s, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
+    rc = advance_and_resolve_enqueue(s, mpc, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
                                iters_out, stats_out);
     use_main(s);  // joins the sub-batch streams
     if (cudaStreamEndCapture(s->stream, &graph) != cudaSuccess || !graph) rc = rc ? rc : IDTO_ERR_CUDA;
@@ -1275,12 +1290,41 @@ int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_gues
     drop_graph(s);
     s->use_graph = false;
     g_launch_counter = l0;
-    return resolve_async_enqueue(s, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
+    return advance_and_resolve_enqueue(s, mpc, max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
                                  iters_out, stats_out);
   }
   IDTO_CUDA_CHECK(cudaGraphLaunch(s->gexec, s->stream));
   s->main_dirty = true;
   return IDTO_OK;
+}
+
+int idto_resolve_async(idto_solver_t s, int max_iterations, const double* q_guess, const double* q_init,
+                       const double* v_init, const double* q_nom, const double* v_nom, double* q_out, double* v_out,
+                       double* tau_out, int* iters_out, double* stats_out) {
+  return resolve_impl(s, MpcArgs(), max_iterations, q_guess, q_init, v_init, q_nom, v_nom, q_out, v_out, tau_out,
+                      iters_out, stats_out);
+}
+
+// One MPC re-plan in one call: idto_mpc_advance followed by idto_resolve_async without new inputs
+// (ModelPredictiveController::UpdateAbstractState, examples/mpc_controller.cc:43-85, is exactly this sequence).
+// With pinned inputs the advance kernel is part of the captured graph of the re-solve; pageable inputs are copied
+// eagerly first (a copy from pageable memory does not belong into a graph that is replayed).
+int idto_mpc_resolve_async(idto_solver_t s, const double* elapsed, const double* q0, const double* v0,
+                           const double* q_nom_selector, int max_iterations, double* q_out, double* v_out,
+                           double* tau_out, int* iters_out, double* stats_out) {
+  if (!s || !elapsed || !q0 || !v0 || max_iterations < 0) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);
+  const bool pinned = mapped_alias(elapsed) && mapped_alias(q0) && mapped_alias(v0) &&
+                      (!q_nom_selector || mapped_alias(q_nom_selector));
+  if (!pinned) {
+    if (int rc = idto_mpc_advance(s, elapsed, q0, v0, q_nom_selector)) return rc;
+    return resolve_impl(s, MpcArgs(), max_iterations, nullptr, nullptr, nullptr, nullptr, nullptr, q_out, v_out,
+                        tau_out, iters_out, stats_out);
+  }
+  MpcArgs m;
+  m.elapsed = elapsed, m.q0 = q0, m.v0 = v0, m.selector = q_nom_selector;
+  return resolve_impl(s, m, max_iterations, nullptr, nullptr, nullptr, nullptr, nullptr, q_out, v_out, tau_out,
+                      iters_out, stats_out);
 }
 
 static int resolve_async_enqueue(idto_solver_t s, int max_iterations, const double* q_guess, const double* q_init,
@@ -1383,10 +1427,8 @@ static int resolve_async_enqueue(idto_solver_t s, int max_iterations, const doub
   return IDTO_OK;
 }
 
-int idto_mpc_advance(idto_solver_t s, const double* elapsed, const double* q0, const double* v0,
-                     const double* q_nom_selector) {
-  if (!s || !elapsed || !q0 || !v0) return IDTO_ERR_INVALID_ARG;
-  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
+static int mpc_advance_enqueue(idto_solver_t s, const MpcArgs& m) {
+  const double *elapsed = m.elapsed, *q0 = m.q0, *v0 = m.v0, *q_nom_selector = m.selector;
   const SolverConsts& c = s->sc;
   const size_t B = c.B;
   use_main(s);
@@ -1413,7 +1455,17 @@ int idto_mpc_advance(idto_solver_t s, const double* elapsed, const double* q0, c
     set_last_error("idto_mpc_advance: horizon too long for the spline workspace");
     return rc;
   }
+  s->main_dirty = true;
   return IDTO_OK;
+}
+
+int idto_mpc_advance(idto_solver_t s, const double* elapsed, const double* q0, const double* v0,
+                     const double* q_nom_selector) {
+  if (!s || !elapsed || !q0 || !v0) return IDTO_ERR_INVALID_ARG;
+  cudaSetDevice(s->device);  // the caller may have changed the current device since creation
+  MpcArgs m;
+  m.elapsed = elapsed, m.q0 = q0, m.v0 = v0, m.selector = q_nom_selector;
+  return mpc_advance_enqueue(s, m);
 }
 
 int idto_fence(idto_solver_t s) {

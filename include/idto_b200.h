@@ -246,6 +246,13 @@ int idto_synchronize(idto_solver_t s);
  * Asynchronous on the solver's stream; follow with idto_resolve_async(..., all inputs NULL). */
 int idto_mpc_advance(idto_solver_t s, const double* elapsed, const double* q0, const double* v0,
                      const double* q_nom_selector);
+/* One MPC re-plan in ONE call: idto_mpc_advance(elapsed, q0, v0, q_nom_selector) followed by
+ * idto_resolve_async(max_iterations, no new inputs, outputs) — the whole of
+ * ModelPredictiveController::UpdateAbstractState (examples/mpc_controller.cc:43-85).  Same results as the two calls;
+ * with pinned input buffers the advance is part of the re-solve's captured graph (one launch from the host). */
+int idto_mpc_resolve_async(idto_solver_t s, const double* elapsed, const double* q0, const double* v0,
+                           const double* q_nom_selector, int max_iterations,
+                           double* q_out, double* v_out, double* tau_out, int* iters_out, double* stats_out);
 /* Stream-ordering point without a host wait: everything enqueued so far (on the internal sub-batch
  * streams too) is ordered before whatever the caller enqueues next on the solver's stream, e.g. a
  * CUDA event record. */

@@ -223,3 +223,49 @@ def test_pinned_host_buffers_take_the_zero_copy_path_with_identical_results(nsub
     for a, b in zip(res["pageable"], res["pinned"]):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned", [False, True])
+def test_mpc_resolve_async_equals_advance_then_resolve(pinned):
+    """idto_mpc_resolve_async (one call per MPC re-plan, examples/mpc_controller.cc:43-85) against idto_mpc_advance +
+    idto_resolve_async: bit-identical solutions over a stream of re-plans (eager, capture, replay), with a q_nom
+    selector, pageable and pinned buffers."""
+    import torch
+    from idto_b200 import capi
+    from idto_b200.types import NUM_STATS
+    m, dt, prob, params, guess = problems.hopper(T=20, gradients_method=GRAD_CENTRAL)
+    B, T1, T = 33, 21, 20
+    q0, v0, qg = problems.perturbed_batch(m, prob, B)
+    model = capi.Model(m)
+    res = {}
+    for kind in ("two_calls", "one_call"):
+        def buf(shape, dtype=torch.float64):
+            t = torch.zeros(shape, dtype=dtype)
+            return t.pin_memory() if pinned else t
+        hsel = buf((m.nq,))
+        hsel.numpy()[0] = 1.0
+        sel = hsel.numpy()
+        hq0, hv0, hel = buf((B, m.nq)), buf((B, m.nv)), buf((B,))
+        hq0.numpy()[:], hv0.numpy()[:] = q0, v0
+        oq, ov, ot, ost = buf((B, T1, m.nq)), buf((B, T1, m.nv)), buf((B, T, m.nv)), buf((B, 2, NUM_STATS))
+        gs = capi.BatchSolver(model, dt, prob, params, B)
+        gs.reset_initial_conditions(q0, v0)
+        gs.set_q(qg)
+        gs.solve(2)
+        outs = []
+        for k in range(4):
+            hel.numpy()[:] = 0.01 * (k + 1)
+            hq0.numpy()[:, 0] = q0[:, 0] + 0.001 * k
+            kw = dict(q_out=oq.data_ptr(), v_out=ov.data_ptr(), tau_out=ot.data_ptr(), stats_out=ost.data_ptr())
+            if kind == "two_calls":
+                gs.mpc_advance(hel.numpy(), hq0.numpy(), hv0.numpy(), sel)
+                gs.resolve_async(2, **kw)
+            else:
+                gs.mpc_resolve_async(hel.numpy(), hq0.numpy(), hv0.numpy(), 2, q_nom_selector=sel, **kw)
+            gs.synchronize()
+            outs.append([x.numpy().copy() for x in (oq, ov, ot, ost)] + [gs.get("q_nom").copy()])
+        res[kind] = outs
+    for a, b in zip(res["two_calls"], res["one_call"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)

@@ -28,11 +28,13 @@ def Bv(): gs.flush_l2(flush.data_ptr(), flush.numel()); gs.invalidate(); gs.reso
 def C(): gs.flush_l2(flush.data_ptr(), flush.numel()); gs.mpc_advance(hel.numpy(), hq0.numpy(), hv0.numpy()); gs.resolve_async(1); gs.synchronize()
 def D(): gs.flush_l2(flush.data_ptr(), flush.numel()); gs.mpc_advance(hel.numpy(), hq0.numpy(), hv0.numpy()); gs.resolve_async(1, **outs); gs.synchronize()
 def E(): gs.mpc_advance(hel.numpy(), hq0.numpy(), hv0.numpy()); gs.resolve_async(1, **outs); gs.synchronize()
+def G(): gs.flush_l2(flush.data_ptr(), flush.numel()); gs.mpc_resolve_async(hel.numpy(), hq0.numpy(), hv0.numpy(), 1, **outs); gs.synchronize()
 def F(): gs.flush_l2(flush.data_ptr(), flush.numel()); gs.synchronize()
 run("resident, no host sync (flush + invalidate + resolve)", A)
 run("  + synchronize every step", A2)
 run("  + D2H of the solution", Bv)
 run("mpc_advance instead of invalidate, sync, no D2H", C)
-run("full e2e step (bench)", D)
+run("full e2e step, two calls (advance, re-solve)", D)
+run("full e2e step, one call (bench)", G)
 run("full e2e step without the L2 flush", E)
 run("L2 flush + sync alone", F)
