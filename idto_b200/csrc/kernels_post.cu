@@ -18,7 +18,7 @@ namespace idto {
 // Trust ratio (cc:1979-2035), acceptance (cc:2550-2553), stats (cc:2586-2598), commit, Delta update (cc:2613-2622).
 // `commit` = 0 only evaluates rho.  One CTA per problem; s.H~s and gm.s come from k_post.
 __global__ void __launch_bounds__(256) k_trust_final(SolverConsts sc, SolverBufs bf, int commit, int near_stride_) {
-  __shared__ double red[32];
+  __shared__ double red[2 * 32];
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, nh = sc.nh;
   ProbCtl* ctl = bf.ctl + b;
   if (!ctl->active) return;
@@ -28,7 +28,11 @@ __global__ void __launch_bounds__(256) k_trust_final(SolverConsts sc, SolverBufs
     if (sc.eq) hl += bf.sc.h[ge] * bf.lambda[ge];
     h2 += bf.st.h[ge] * bf.st.h[ge];
   }
-  hl = block_sum(hl, red), h2 = block_sum(h2, red);
+  {
+    double v[2] = {hl, h2};
+    block_sum_n(v, red);
+    hl = v[0], h2 = v[1];
+  }
   const double ht = ctl->ht, gt = ctl->gt;  // k_dogleg_post
   const double merit_k = bf.merit[b];
   const double merit_kp = bf.sc.cost[b] + hl;

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kRowThreads) k_gm_matvec(SolverConsts sc, Solv
 // steps); branch logic, dq, dqH, logging scalars, and the
 // scratch trajectory q + dq (cc:1991-1993).
 __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs bf) {
-  __shared__ double red[32];
+  __shared__ double red[5 * 32];
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, n = sc.n;
   ProbCtl* ctl = bf.ctl + b;
   if (!ctl->active) return;
@@ -169,8 +169,11 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
     a += d * d, bq += pu * d;
     xg += ph * gm[e];
   }
-  pU2 = block_sum(pU2, red), pH2 = block_sum(pH2, red), a = block_sum(a, red), bq = block_sum(bq, red);
-  xg = block_sum(xg, red);  // gm . pH
+  {
+    double v[5] = {pU2, pH2, a, bq, xg};  // (xg = gm . pH)
+    block_sum_n(v, red);
+    pU2 = v[0], pH2 = v[1], a = v[2], bq = v[3], xg = v[4];
+  }
   const double pUn = sqrt(pU2), pHn = sqrt(pH2);
   int active;
   double s = 0.0;
@@ -211,7 +214,11 @@ __global__ void __launch_bounds__(256) k_dogleg_post(SolverConsts sc, SolverBufs
     q2 += q[e] * q[e];
     qs[e] = q[e] + x;  // scratch_state.set_q(q); AddToQ(dq)
   }
-  dq2 = block_sum(dq2, red), dqH2 = block_sum(dqH2, red), gdq = block_sum(gdq, red), q2 = block_sum(q2, red);
+  {
+    double v[4] = {dq2, dqH2, gdq, q2};
+    block_sum_n(v, red);
+    dq2 = v[0], dqH2 = v[1], gdq = v[2], q2 = v[3];
+  }
   __syncthreads();
   if (sc.normalize_quat) {  // cc:1993 + cc:2691-2707
     for (int idx = tid; idx < (sc.T + 1) * sc.nquat; idx += nt) {

@@ -23,4 +23,25 @@ __device__ __forceinline__ double block_sum(double x, double* red) {
   return t;
 }
 
+// N sums at once: one pair of barriers instead of N (each value is added up in exactly the order block_sum uses, so
+// the results are bit-identical to N separate calls).  `red` holds >= 32 * N doubles.
+template <int N>
+__device__ __forceinline__ void block_sum_n(double (&x)[N], double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int j = 0; j < N; ++j) x[j] = warp_sum(x[j]);
+  __syncthreads();  // protect `red` from a previous call
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) red[j * 32 + wid] = x[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += red[j * 32 + i];
+    x[j] = t;
+  }
+}
+
 }  // namespace idto
