@@ -140,3 +140,19 @@ def test_top_level_pyidto_module_reexports_the_binding():
         assert getattr(pyidto, name) is getattr(impl, name)
     p = pyidto.SolverParameters()
     assert p.max_iterations == 100 and p.Delta0 == 1e-1  # python_bindings/test/solver_parameters_test.py
+
+
+def test_python_constants_match_the_header_enums():
+    """idto_b200/types.py restates the enums of include/idto_b200.h: every IDTO_<GROUP>_<NAME> = value there must
+    equal <GROUP>_<NAME> here (gradient methods, scaling methods, linear solvers, status codes)."""
+    import re
+    from idto_b200 import types as T
+    hdr = open(os.path.join(ROOT, "include", "idto_b200.h")).read()
+    found = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"IDTO_([A-Z0-9_]+)\s*=\s*(-?\d+)", hdr))
+    checked = 0
+    for name, val in found.items():
+        for prefix in ("GRAD_", "SCALING_", "LINSOLVE_"):
+            if name.startswith(prefix):
+                assert getattr(T, name) == val, name
+                checked += 1
+    assert checked >= 11 and found["LINSOLVE_CYCLIC_REDUCTION"] == 3
